@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- RD-map + OS-CFAR throughput (CPIs/s) of the B200 path, BASELINE.json config 3.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                           (CPU arm: the NumPy oracle)
+
+One "step" = one pass of the whole hot path (window -> range FFT -> corner turn -> Doppler
+FFT -> magnitude -> 2D OS-CFAR -> sorted detection list) over the per-GPU batch of synthetic
+CPIs resident in HBM.  `value` = CPIs all ranks processed / max-over-ranks device time.
+`e2e` = the same metric through RadarCore.process() with pinned HOST buffers (H2D of the
+cube and D2H of the detection list inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rd_map_os_cfar_cpis_per_sec"
+UNIT = "CPI/s"
+N_CH, N_CHIRPS, N_SAMPLES = 12, 256, 512            # BASELINE.json configs[2]: automotive MIMO
+CELLS = N_CH * N_CHIRPS * N_SAMPLES
+# algorithmic HBM bytes per cell (SURVEY.md 8d / DESIGN.md): K1 = B_in + 8, K2 = 8 + 4, K3 = 4
+BYTES_PER_CELL = {"range": {"int16": 12, "complex64": 16}, "doppler": 12, "cfar": 4}
+
+
+def workload_name(fmt, n_cpi):
+    return f"automotive_mimo_{N_CHIRPS}x{N_SAMPLES}x{N_CH}ch_{fmt}_batch{n_cpi}"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 8] or [r for (_, r) in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+
+
+def make_unique_cpis(n_unique, fmt):
+    from oracle import stimulus as st            # synthetic input generator only (not timed, not the product path)
+    cube, _ = st.synthetic_cube(n_unique, N_CH, N_CHIRPS, N_SAMPLES, seed=1234, dtype=fmt)
+    return cube
+
+
+def cpu_reference_step(cubes, pool=None):
+    """The oracle's float path (NumPy) over `cubes`; with a pool, CPIs are spread over processes."""
+    from oracle import float_path as fp
+    if pool is None:
+        return [fp.process_cpi(c) for c in cubes]
+    return pool.map(_cpu_one, list(cubes))
+
+
+def _cpu_one(c):
+    from oracle import float_path as fp
+    m, d = fp.process_cpi(c)
+    return len(d)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself is
+    VHDL + closed Xilinx FFT IP and cannot run here; its CPU restatement (oracle/, NumPy) is timed,
+    all host threads it can use (one process per core, CPIs spread over them)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    n_sample = procs                                   # one CPI (12 channels) per process per step
+    cube = make_unique_cpis(min(n_sample, 4), args.fmt)
+    cubes = [cube[i % cube.shape[0]] for i in range(n_sample)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        for _ in range(max(1, min(args.warmup, 1))):
+            cpu_reference_step(cubes, pool)
+        steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_reference_step(cubes, pool)
+        dt = time.perf_counter() - t0
+    value = n_sample * steps / dt
+    sample = f"{n_sample} CPIs x {N_CH} ch per step over {procs} processes, {steps} steps (bounded sample of the batch)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(args.fmt, args.cpis)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpis", type=int, default=1024, help="CPIs per GPU per step (BASELINE config 3: 1024)")
+    ap.add_argument("--fmt", default="int16", choices=["int16", "complex64"])
+    ap.add_argument("--chunk", type=int, default=0, help="CPIs per internal pass (0 = auto, L2-sized)")
+    ap.add_argument("--e2e-cpis", type=int, default=256)
+    ap.add_argument("--unique", type=int, default=8, help="distinct synthetic CPIs tiled over the batch")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import fpga_fmcw_radar_processor_b200 as rdp
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier_max(ms):
+        if dist is None:
+            return ms
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_cpi = args.cpis
+    core = rdp.RadarCore(n_range=N_SAMPLES, n_doppler=N_CHIRPS, n_channels=N_CH, input_format=args.fmt,
+                         max_cpis=max(n_cpi, args.e2e_cpis), chunk_cpis=args.chunk, device=local_rank)
+    info = core.info()
+
+    # ---- synthetic batch, resident in HBM before the timed region ----------------------------
+    uniq = make_unique_cpis(min(args.unique, n_cpi), args.fmt)
+    per_cpi = core.in_bytes_per_cpi
+    d_cube = core.device_buffer(n_cpi * per_cpi)
+    import ctypes as C
+    for i in range(0, n_cpi, uniq.shape[0]):
+        n = min(uniq.shape[0], n_cpi - i)
+        core._check(core.lib.rdp_copy_h2d(core.h, C.c_void_p(d_cube.ptr.value + i * per_cpi),
+                                          C.c_void_p(uniq.ctypes.data), n * per_cpi))
+    d_dets = core.device_buffer(n_cpi * core.max_dets_per_cpi * rdp.DET_DTYPE.itemsize)
+    d_cnt, d_st = core.device_buffer(n_cpi * 4), core.device_buffer(n_cpi * 4)
+
+    def step():
+        core.process_device(d_cube, n_cpi, None, d_dets, d_cnt, d_st)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    core.sync()
+    barrier_max(0.0)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = core.info()["kernel_launches"]
+    w0 = time.time()
+    core.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = core.timer_stop()
+    w1 = time.time()
+    launches = core.info()["kernel_launches"] - l0
+    ms = barrier_max(ms)
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    value = world * n_cpi * args.steps / (ms * 1e-3)
+    counts = d_cnt.download((n_cpi,), np.int32)
+    status = d_st.download((n_cpi,), np.uint32)
+
+    # ---- per-kernel durations (events on the launching stream around every launch) -----------
+    core.stage_timing()
+    core.set_stage_timing(True)
+    for _ in range(2):
+        step()
+    st_t = core.stage_timing()
+    core.set_stage_timing(False)
+    peak, peak_src = measured_peak()
+    stages = {}
+    for name in ("range", "doppler", "cfar"):
+        bpc = BYTES_PER_CELL[name][args.fmt] if name == "range" else BYTES_PER_CELL[name]
+        t = st_t[name]
+        if t["launches"]:
+            avg_ms = t["ms"] / t["launches"]
+            cells_per_launch = 2.0 * n_cpi * CELLS / t["launches"]
+            gbs = cells_per_launch * bpc / (avg_ms * 1e-3) / 1e9
+            stages[name] = {"ms_total_per_step": t["ms"] / 2.0, "launches_per_step": t["launches"] // 2,
+                            "avg_launch_ms": avg_ms, "alg_bytes_per_cell": bpc, "achieved_gbs": gbs, "frac": gbs / peak}
+    stages["sort"] = {"ms_total_per_step": st_t["sort"]["ms"] / 2.0, "launches_per_step": st_t["sort"]["launches"] // 2}
+    dom = max(("range", "doppler", "cfar"), key=lambda k: stages.get(k, {}).get("ms_total_per_step", 0.0))
+    kernel_names = {"range": "k1_range_kernel", "doppler": "k2_doppler_kernel", "cfar": "k3_cfar_kernel"}
+    roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": stages[dom]["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": ncu_traffic(kernel_names[dom]),
+                "peak_source": peak_src, "stages": stages,
+                "note": "K3 (OS-CFAR, 128 reference cells per cell) is ALU-bound, not HBM-bound; see DESIGN.md"}
+
+    # ---- end to end: pinned host cube in, detection list out, copies inside the timed region --
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_cpis, n_cpi)
+        host = core.pinned_empty((ne,) + uniq.shape[1:], uniq.dtype)
+        for i in range(ne):
+            host[i] = uniq[i % uniq.shape[0]]
+        core.process(host, want_map=False)
+        barrier_max(0.0)
+        reps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(reps):
+            _, dets, nd, _ = core.process(host, want_map=False)
+            d2h = dets.nbytes + nd.nbytes * 2
+        dt = (time.perf_counter() - t0) * 1e3
+        dt = barrier_max(dt)
+        e2e = {"value": world * ne * reps / (dt * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host.nbytes),
+               "d2h_bytes_per_step": int(d2h), "cpis_per_step": ne, "steps": reps,
+               "api": "RadarCore.process (rdp_process_host), pinned host buffers"}
+
+    # ---- CPU baseline on this box's host cores (bounded sample, rank 0, N = 1 only) ----------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = uniq[:2]
+        t0 = time.perf_counter()
+        cpu_reference_step(sample)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample.shape[0] / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{sample.shape[0]} CPIs x {N_CH} ch of the same workload through the NumPy oracle, one process "
+                         f"(host has {os.cpu_count()} cores)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args.fmt, n_cpi), "cpis_per_gpu_per_step": n_cpi,
+                           "unique_cpis": int(uniq.shape[0]), "chunk_cpis": info["chunk_cpis"],
+                           "cfar": "ref 4/4 guard 2/1 rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
+                           "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),
+                           "device": info["device_name"], "sharding": "CPIs dealt to ranks, no data-path collective"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu,
+                "detections_per_cpi_mean": float(counts.mean()), "status_or": int(np.bitwise_or.reduce(status))}
+        print(json.dumps(line), flush=True)
+    core.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

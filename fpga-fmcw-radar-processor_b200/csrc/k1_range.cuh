@@ -1,0 +1,100 @@
+// k1_range.cuh -- K1: range window (x) range FFT (x) corner turn, one pass over the cube.
+//
+// Replaces window_multiplier (N_SAMPLES = N_RANGE) -> xfft_range -> corner_turner of
+// rtl/src/radar_core.vhd:267-327.  A CTA owns a tile of TC consecutive chirps of one
+// (CPI, channel): each FFT group transforms one chirp at a time in registers and drops the
+// spectrum into a padded shared-memory tile [range][chirp]; the tile is then written out
+// range-major ([range][chirp], corner_turner.vhd:79-80) as TC*8-byte contiguous segments,
+// so the transpose costs no extra pass over HBM.
+//   algorithmic HBM bytes / cell: B_in (4 int16-IQ | 8 complex64) read + 8 written.
+#pragma once
+#include "fft_core.cuh"
+
+namespace rdp {
+
+template <class Plan>
+struct K1Shape {
+    static constexpr int THREADS = (Plan::T >= 256) ? Plan::T : 256;
+    static constexpr int G = THREADS / Plan::T;           // transforms in flight per CTA
+    // chirps per tile: 128-byte output segments (16 x complex64) unless shared memory forbids
+    static constexpr int TC_MAX = (Plan::N <= 1024) ? (G > 16 ? G : 16) : (Plan::N == 2048 ? 8 : 4);
+    static __host__ __device__ constexpr size_t smem_bytes(int tile_chirps) {
+        return sizeof(float2) * ((size_t)Plan::N * (tile_chirps + 1) + (size_t)G * Plan::XBUFS);
+    }
+};
+
+__device__ __forceinline__ float2 load_sample_i16(const uint32_t* __restrict__ p, long long idx) {
+    uint32_t w = __ldg(p + idx);                           // {Q[31:16], I[15:0]}  window_multiplier.vhd:93-94
+    return make_float2((float)(short)(w & 0xffffu), (float)((int)w >> 16));
+}
+
+template <class Plan, int IN_FMT>
+__global__ void __launch_bounds__(K1Shape<Plan>::THREADS)
+k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
+                const float* __restrict__ window, const float2* __restrict__ twtab,
+                int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles) {
+    constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
+    constexpr int G = K1Shape<Plan>::G, THREADS = K1Shape<Plan>::THREADS;
+    using P0 = typename Plan::P0;
+    using PL = typename Plan::LAST;
+    RDP_DYN_SMEM(smem_raw);
+    float2* tile = reinterpret_cast<float2*>(smem_raw);
+    const int tcp = tile_chirps + 1;                       // +1 complex: conflict-free column writes
+    float2* xbuf = tile + (size_t)N * tcp + (size_t)(threadIdx.x / T) * Plan::XBUFS;
+    const int tid = threadIdx.x % T, gid = threadIdx.x / T;
+
+    float2 tw[Plan::NTW > 0 ? Plan::NTW : 1];
+    Plan::load_twiddles(tw, twtab, tid);
+    float wv[E];
+    RDP_UNROLL
+    for (int b = 0; b < P0::NB; ++b) {
+        RDP_UNROLL
+        for (int r = 0; r < P0::R; ++r) wv[b * P0::R + r] = __ldg(window + P0::in_index(tid, b, r));
+    }
+    int parity = 0;
+    const int iters = (tile_chirps + G - 1) / G;
+
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const long long map = t / tiles_per_map;
+        const int c0 = (int)(t % tiles_per_map) * tile_chirps;
+        for (int it = 0; it < iters; ++it) {
+            const int c = it * G + gid;
+            const bool active = c < tile_chirps;
+            float2 v[E];
+            const long long base = ((map * n_chirps) + c0 + c) * (long long)N;
+            RDP_UNROLL
+            for (int b = 0; b < P0::NB; ++b) {
+                RDP_UNROLL
+                for (int r = 0; r < P0::R; ++r) {
+                    float2 s = make_float2(0.f, 0.f);
+                    if (active) {
+                        const long long idx = base + P0::in_index(tid, b, r);
+                        if (IN_FMT == 0) s = load_sample_i16(reinterpret_cast<const uint32_t*>(cube), idx);
+                        else s = __ldg(reinterpret_cast<const float2*>(cube) + idx);
+                    }
+                    const float w = wv[b * P0::R + r];
+                    v[b * P0::R + r] = make_float2(s.x * w, s.y * w);
+                }
+            }
+            Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
+            if (active) {
+                RDP_UNROLL
+                for (int b = 0; b < PL::NB; ++b) {
+                    RDP_UNROLL
+                    for (int r = 0; r < PL::R; ++r) tile[PL::out_index(tid, b, r) * tcp + c] = v[b * PL::R + r];
+                }
+            }
+        }
+        __syncthreads();
+        // range-major store: row k of the tile -> x_rc[map][k][c0 .. c0+tile_chirps)
+        float2* dst = x_rc + map * (long long)N * n_chirps + c0;
+        const int total = N * tile_chirps;
+        for (int i = threadIdx.x; i < total; i += THREADS) {
+            const int k = i / tile_chirps, c = i % tile_chirps;
+            dst[(long long)k * n_chirps + c] = tile[k * tcp + c];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace rdp

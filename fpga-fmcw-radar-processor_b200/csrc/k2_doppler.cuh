@@ -1,0 +1,97 @@
+// k2_doppler.cuh -- K2: (MTI) (x) Doppler window (x) Doppler FFT (x) magnitude.
+//
+// Replaces doppler_notch -> window_multiplier (N_SAMPLES = N_DOPPLER) -> xfft_doppler ->
+// magnitude_calc of rtl/src/radar_core.vhd:329-374.  One FFT group per range line of the
+// range-major intermediate; the magnitude is formed in registers and written as float32
+// [range][doppler] (Doppler bin 0 = zero Doppler, natural order).
+//   algorithmic HBM bytes / cell: 8 read + 4 written.
+#pragma once
+#include "fft_core.cuh"
+
+namespace rdp {
+
+template <class Plan>
+struct K2Shape {
+    static constexpr int THREADS = (Plan::T >= 256) ? Plan::T : 256;
+    static constexpr int G = THREADS / Plan::T;
+    static __host__ __device__ constexpr size_t smem_bytes() {
+        return sizeof(float2) * ((size_t)G * Plan::XBUFS) + 16;
+    }
+};
+
+template <int MAG>
+__device__ __forceinline__ float magnitude(float2 z) {
+    if (MAG == 0) {                                      // alpha-max-beta-min, magnitude_calc.vhd:55-60,78-81
+        float ai = fabsf(z.x), aq = fabsf(z.y);
+        float mx = fmaxf(ai, aq), mn = fminf(ai, aq);
+        return mx + 0.375f * mn;                         // min>>2 + min>>3 == 0.375 * min
+    }
+    float p = z.x * z.x + z.y * z.y;
+    if (MAG == 1) return sqrtf(p);
+    if (MAG == 2) return p;
+    return 10.0f * log10f(fmaxf(p, 1e-30f));
+}
+
+template <class Plan, int MAG>
+__global__ void __launch_bounds__(K2Shape<Plan>::THREADS)
+k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
+                  const float* __restrict__ window, const float2* __restrict__ twtab,
+                  long long n_rows, int mti_mode) {
+    constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
+    constexpr int G = K2Shape<Plan>::G;
+    using P0 = typename Plan::P0;
+    using PL = typename Plan::LAST;
+    RDP_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x % T, gid = threadIdx.x / T;
+    float2* xbuf = reinterpret_cast<float2*>(smem_raw) + (size_t)gid * Plan::XBUFS;
+
+    float2 tw[Plan::NTW > 0 ? Plan::NTW : 1];
+    Plan::load_twiddles(tw, twtab, tid);
+    float wv[E];
+    RDP_UNROLL
+    for (int b = 0; b < P0::NB; ++b) {
+        RDP_UNROLL
+        for (int r = 0; r < P0::R; ++r) wv[b * P0::R + r] = __ldg(window + P0::in_index(tid, b, r));
+    }
+    int parity = 0;
+
+    for (long long row0 = (long long)blockIdx.x * G; row0 < n_rows; row0 += (long long)gridDim.x * G) {
+        const long long row = row0 + gid;
+        const bool active = row < n_rows;
+        const float2* src = x_rc + row * N;
+        float2 v[E];
+        RDP_UNROLL
+        for (int b = 0; b < P0::NB; ++b) {
+            RDP_UNROLL
+            for (int r = 0; r < P0::R; ++r) {
+                const int n = P0::in_index(tid, b, r);
+                float2 s = make_float2(0.f, 0.f);
+                if (active) {
+                    s = __ldg(src + n);
+                    if (mti_mode != 0) {                 // doppler_notch.vhd:72-93, zero initial state (:99-102)
+                        float2 d1 = (n >= 1) ? __ldg(src + n - 1) : make_float2(0.f, 0.f);
+                        if (mti_mode == 2) {
+                            s = csub(s, d1);
+                        } else {
+                            float2 d2 = (n >= 2) ? __ldg(src + n - 2) : make_float2(0.f, 0.f);
+                            s = make_float2(s.x - 2.0f * d1.x + d2.x, s.y - 2.0f * d1.y + d2.y);
+                        }
+                    }
+                }
+                const float w = wv[b * P0::R + r];
+                v[b * P0::R + r] = make_float2(s.x * w, s.y * w);
+            }
+        }
+        Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
+        if (active) {
+            float* dst = rd_map + row * N;
+            RDP_UNROLL
+            for (int b = 0; b < PL::NB; ++b) {
+                RDP_UNROLL
+                for (int r = 0; r < PL::R; ++r) dst[PL::out_index(tid, b, r)] = magnitude<MAG>(v[b * PL::R + r]);
+            }
+        }
+    }
+}
+
+}  // namespace rdp

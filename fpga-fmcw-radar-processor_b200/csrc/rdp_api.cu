@@ -1,0 +1,825 @@
+// rdp_api.cu -- the C ABI of librdp (include/rdp.h) and the host-side launch logic.
+//
+// Built two ways from the same source:
+//   nvcc -gencode arch=compute_100a,code=sm_100a ...      -> librdp.so      (the product)
+//   g++  -x c++ -DRDP_EMU ...                              -> librdp_emu.so  (CPU test harness
+//        for kernel logic only; see csrc/emu/cuda_emu.h -- never loaded by the product)
+#include "../../include/rdp.h"
+#include "k1_range.cuh"
+#include "k2_doppler.cuh"
+#include "k3_cfar.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace rdp;
+
+namespace {
+
+std::string g_create_error;
+
+struct StageEvent { int stage; cudaEvent_t a, b; };
+
+struct K1Launcher {
+    int T, G, tc_max;
+    size_t (*smem)(int tile_chirps);
+    cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
+    void (*launch)(int grid, size_t smem, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
+                   const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles);
+};
+struct K2Launcher {
+    int T, G;
+    size_t smem;
+    cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
+    void (*launch)(int grid, size_t smem, cudaStream_t st, const float2* x_rc, float* rd_map, const float* win,
+                   const float2* tw, long long n_rows, int mti_mode);
+};
+struct K3Launcher {
+    int trows, tcols;            // 0,0 => generic kernel
+    size_t smem;
+    cudaError_t (*prepare)(size_t smem);
+    void (*launch)(long long grid, size_t smem, cudaStream_t st, const float* rd_map, float* cfar_out, rdp_det* dets,
+                   int* counts, CfarArgs a, int tiles_r, int tiles_c);
+};
+
+template <class K>
+cudaError_t prepare_kernel(K kernel, int threads, size_t smem, int* ctas_per_sm) {
+    cudaError_t e = cudaSuccess;
+#ifndef RDP_EMU
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int n = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
+    if (ctas_per_sm) *ctas_per_sm = n < 1 ? 1 : n;
+#else
+    (void)kernel; (void)threads; (void)smem;
+    if (ctas_per_sm) *ctas_per_sm = 1;
+#endif
+    return e;
+}
+
+// ---- K1 dispatch ---------------------------------------------------------------------------
+template <class Plan, int FMT>
+struct K1Inst {
+    static size_t smem(int tc) { return K1Shape<Plan>::smem_bytes(tc); }
+    static cudaError_t prepare(size_t s, int* occ) {
+        return prepare_kernel(k1_range_kernel<Plan, FMT>, K1Shape<Plan>::THREADS, s, occ);
+    }
+    static void launch(int grid, size_t s, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
+                       const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles) {
+        RDP_LAUNCH((k1_range_kernel<Plan, FMT>), grid, K1Shape<Plan>::THREADS, s, st, cube, x_rc, win, tw,
+                   n_chirps, tile_chirps, tiles_per_map, total_tiles);
+    }
+    static K1Launcher get() {
+        return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch};
+    }
+};
+
+template <class Plan, int MAG>
+struct K2Inst {
+    static cudaError_t prepare(size_t s, int* occ) {
+        return prepare_kernel(k2_doppler_kernel<Plan, MAG>, K2Shape<Plan>::THREADS, s, occ);
+    }
+    static void launch(int grid, size_t s, cudaStream_t st, const float2* x_rc, float* rd_map, const float* win,
+                       const float2* tw, long long n_rows, int mti_mode) {
+        RDP_LAUNCH((k2_doppler_kernel<Plan, MAG>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
+                   n_rows, mti_mode);
+    }
+    static K2Launcher get() {
+        return K2Launcher{Plan::T, K2Shape<Plan>::G, K2Shape<Plan>::smem_bytes(), &prepare, &launch};
+    }
+};
+
+// FFT plans per length (see fft_core.cuh): radix <= 8 with 8 points / thread up to 512,
+// radix 16 with 16 points / thread (single-buffered exchange from 2048) above.
+using Plan8 = FftPlan<8, 8, 8>;
+using Plan16 = FftPlan<16, 8, 8, 2>;
+using Plan32 = FftPlan<32, 8, 8, 4>;
+using Plan64 = FftPlan<64, 8, 8, 8>;
+using Plan128 = FftPlan<128, 8, 8, 4, 4>;
+using Plan256 = FftPlan<256, 8, 8, 8, 4>;
+using Plan512 = FftPlan<512, 8, 8, 8, 8>;
+using Plan1024 = FftPlan<1024, 16, 16, 16, 4>;
+using Plan2048 = FftPlan<2048, 16, 16, 16, 8, 1, 0>;
+using Plan4096 = FftPlan<4096, 16, 16, 16, 16, 1, 0>;
+
+template <int FMT>
+bool k1_for(int n, K1Launcher* out) {
+    switch (n) {
+        case 8: *out = K1Inst<Plan8, FMT>::get(); return true;
+        case 16: *out = K1Inst<Plan16, FMT>::get(); return true;
+        case 32: *out = K1Inst<Plan32, FMT>::get(); return true;
+        case 64: *out = K1Inst<Plan64, FMT>::get(); return true;
+        case 128: *out = K1Inst<Plan128, FMT>::get(); return true;
+        case 256: *out = K1Inst<Plan256, FMT>::get(); return true;
+        case 512: *out = K1Inst<Plan512, FMT>::get(); return true;
+        case 1024: *out = K1Inst<Plan1024, FMT>::get(); return true;
+        case 2048: *out = K1Inst<Plan2048, FMT>::get(); return true;
+        case 4096: *out = K1Inst<Plan4096, FMT>::get(); return true;
+    }
+    return false;
+}
+template <int MAG>
+bool k2_for(int n, K2Launcher* out) {
+    switch (n) {
+        case 8: *out = K2Inst<Plan8, MAG>::get(); return true;
+        case 16: *out = K2Inst<Plan16, MAG>::get(); return true;
+        case 32: *out = K2Inst<Plan32, MAG>::get(); return true;
+        case 64: *out = K2Inst<Plan64, MAG>::get(); return true;
+        case 128: *out = K2Inst<Plan128, MAG>::get(); return true;
+        case 256: *out = K2Inst<Plan256, MAG>::get(); return true;
+        case 512: *out = K2Inst<Plan512, MAG>::get(); return true;
+        case 1024: *out = K2Inst<Plan1024, MAG>::get(); return true;
+        case 2048: *out = K2Inst<Plan2048, MAG>::get(); return true;
+        case 4096: *out = K2Inst<Plan4096, MAG>::get(); return true;
+    }
+    return false;
+}
+
+// ---- K3 dispatch ---------------------------------------------------------------------------
+template <int HL, int HC, int GL, int GC, int S, int TCOLS>
+struct K3Inst {
+    using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
+    static cudaError_t prepare(size_t s) {
+        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>, 256, s, nullptr);
+    }
+    static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out, rdp_det* dets,
+                       int* counts, CfarArgs a, int tiles_r, int tiles_c) {
+        RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>), (unsigned)grid, 256, s, st, rd_map, cfar_out, dets,
+                   counts, a, tiles_r, tiles_c);
+    }
+    static K3Launcher get() { return K3Launcher{Sh::TROWS, TCOLS, Sh::smem_bytes(), &prepare, &launch}; }
+};
+struct K3Generic {
+    static cudaError_t prepare(size_t) { return cudaSuccess; }
+    static void launch(long long grid, size_t, cudaStream_t st, const float* rd_map, float* cfar_out, rdp_det* dets,
+                       int* counts, CfarArgs a, int, int) {
+        long long n_cells = grid;   // grid carries the cell count for the generic kernel
+        long long blocks = (n_cells + 7) / 8;
+        if (blocks > 148 * 64) blocks = 148 * 64;
+        RDP_LAUNCH(k3_cfar_generic_kernel, (unsigned)blocks, 256, 0, st, rd_map, cfar_out, dets, counts, a, n_cells);
+    }
+    static K3Launcher get() { return K3Launcher{0, 0, 0, &prepare, &launch}; }
+};
+
+K3Launcher k3_for(int hl, int hc, int gl, int gc) {
+#define RDP_K3_CASE(HL, HC, GL, GC, S, TC) \
+    if (hl == HL && hc == HC && gl == GL && gc == GC) return K3Inst<HL, HC, GL, GC, S, TC>::get();
+    RDP_K3_CASE(5, 6, 1, 2, 8, 64)      // radar_core.vhd:376-382 defaults (4,4,2,1), as built
+    RDP_K3_CASE(6, 5, 2, 1, 8, 64)      // same, as named
+    RDP_K3_CASE(3, 4, 1, 1, 8, 64)      // tb_os_cfar_2d.vhd:16-19 (3,2,1,1), as built
+    RDP_K3_CASE(4, 3, 1, 1, 8, 64)      // same, as named
+    RDP_K3_CASE(3, 3, 1, 1, 8, 64)      // legacy quick config (2,2,1,1)
+    RDP_K3_CASE(10, 12, 2, 4, 8, 64)    // BASELINE config 4 "wide" (8,8,4,2), as built
+    RDP_K3_CASE(12, 10, 4, 2, 8, 64)    // same, as named
+#undef RDP_K3_CASE
+    return K3Generic::get();
+}
+
+}  // namespace
+
+struct rdp_handle {
+    rdp_config cfg;
+    int device = 0;
+    int sm_count = 0;
+    int chunk = 1;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    std::vector<cudaEvent_t> ev_copied, ev_done, ev_mapout;
+    float *win_r = nullptr, *win_d = nullptr;
+    float2 *tw_r = nullptr, *tw_d = nullptr;
+    float2* x_rc = nullptr;        // [chunk][channel][range][chirp]
+    float* map_scratch[2] = {nullptr, nullptr};
+    void* in_stage[2] = {nullptr, nullptr};
+    int* counts = nullptr;         // [max_cpis]
+    uint32_t* status = nullptr;    // [max_cpis]
+    rdp_det* dets = nullptr;       // [max_cpis][max_dets]   (host path)
+    rdp_det* packed = nullptr;     // packed list            (host path)
+    void* l2_flush = nullptr;
+    size_t l2_flush_bytes = 0;
+    int64_t scratch_bytes = 0;
+    int64_t launches = 0;
+    K1Launcher k1;
+    K2Launcher k2;
+    K3Launcher k3;
+    int k1_grid_cap = 1, k2_grid_cap = 1;
+    int k1_tile_chirps = 1;
+    size_t k1_smem = 0;
+    CfarArgs cfar;
+    int sort_pow2 = 2;
+    bool stage_timing = false;
+    std::vector<StageEvent> stage_events;
+    float stage_ms[4] = {0, 0, 0, 0};
+    int64_t stage_launches[4] = {0, 0, 0, 0};
+    std::string err;
+};
+
+namespace {
+
+int fail(rdp_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define RDP_CUDA(h, expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? RDP_E_NOMEM : RDP_E_CUDA,        \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+size_t in_bytes_per_sample(const rdp_config& c) { return c.input_format == RDP_IN_INT16_IQ ? 4 : 8; }
+size_t cells_per_cpi(const rdp_config& c) { return (size_t)c.n_channels * c.n_chirps * c.n_samples; }
+
+template <class T>
+int dev_alloc(rdp_handle* h, T** p, size_t count) {
+    void* v = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    RDP_CUDA(h, cudaMalloc(&v, bytes));
+    *p = reinterpret_cast<T*>(v);
+    h->scratch_bytes += (int64_t)bytes;
+    return RDP_OK;
+}
+
+void stage_begin(rdp_handle* h, int stage) {
+    h->launches += 1;
+    h->stage_launches[stage] += 1;
+    if (!h->stage_timing) return;
+    StageEvent se;
+    se.stage = stage;
+    cudaEventCreate(&se.a);
+    cudaEventCreate(&se.b);
+    cudaEventRecord(se.a, h->stream);
+    h->stage_events.push_back(se);
+}
+void stage_end(rdp_handle* h) {
+    if (!h->stage_timing) return;
+    cudaEventRecord(h->stage_events.back().b, h->stream);
+}
+
+int launch_check(rdp_handle* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, RDP_E_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return RDP_OK;
+}
+
+// ---- the three stages on device buffers (n_cpi <= any; no chunking here) -------------------
+int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc) {
+    const rdp_config& c = h->cfg;
+    const int tc = h->k1_tile_chirps;
+    const int tiles_per_map = c.n_chirps / tc;
+    const long long total = (long long)n_cpi * c.n_channels * tiles_per_map;
+    if (total == 0) return RDP_OK;
+    int grid = (int)(total < h->k1_grid_cap ? total : h->k1_grid_cap);
+    stage_begin(h, 0);
+    h->k1.launch(grid, h->k1_smem, h->stream, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total);
+    stage_end(h);
+    return launch_check(h, "k1_range_kernel");
+}
+
+int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map) {
+    const rdp_config& c = h->cfg;
+    const long long rows = (long long)n_cpi * c.n_channels * c.n_samples;
+    if (rows == 0) return RDP_OK;
+    long long blocks = (rows + h->k2.G - 1) / h->k2.G;
+    int grid = (int)(blocks < h->k2_grid_cap ? blocks : h->k2_grid_cap);
+    stage_begin(h, 1);
+    h->k2.launch(grid, h->k2.smem, h->stream, x_rc, rd_map, h->win_d, h->tw_d, rows, c.mti_mode);
+    stage_end(h);
+    return launch_check(h, "k2_doppler_kernel");
+}
+
+// counts must be zeroed by the caller; cpi_base offsets the CPI index written into records
+int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp_det* dets, int* counts) {
+    const rdp_config& c = h->cfg;
+    const long long maps = (long long)n_cpi * c.n_channels;
+    if (maps == 0) return RDP_OK;
+    stage_begin(h, 2);
+    if (h->k3.trows == 0) {
+        h->k3.launch(maps * c.n_samples * c.n_chirps, 0, h->stream, rd_map, cfar_out, dets, counts, h->cfar, 0, 0);
+    } else {
+        const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
+        const int tiles_c = (c.n_chirps + h->k3.tcols - 1) / h->k3.tcols;
+        h->k3.launch(maps * tiles_r * tiles_c, h->k3.smem, h->stream, rd_map, cfar_out, dets, counts, h->cfar,
+                     tiles_r, tiles_c);
+    }
+    stage_end(h);
+    return launch_check(h, "k3_cfar_kernel");
+}
+
+int run_sort(rdp_handle* h, rdp_det* dets, const int* counts, uint32_t* status, int n_cpi) {
+    if (n_cpi == 0) return RDP_OK;
+    stage_begin(h, 3);
+    size_t smem = (size_t)h->sort_pow2 * (sizeof(unsigned long long) + sizeof(float));
+    RDP_LAUNCH(k4_sort_dets_kernel, n_cpi, 256, smem, h->stream, dets, counts, status, h->cfg.max_dets_per_cpi,
+               h->sort_pow2);
+    stage_end(h);
+    return launch_check(h, "k4_sort_dets_kernel");
+}
+
+__global__ void __launch_bounds__(256)
+k5_pack_dets_kernel(const rdp_det* __restrict__ dets, const int* __restrict__ counts, rdp_det* __restrict__ packed,
+                    int max_dets, int cpi_offset) {
+    // one CTA per CPI: offset = sum of the clipped counts of the CPIs before it
+    __shared__ long long offset_sh;
+    const int cpi = blockIdx.x;
+    if (threadIdx.x == 0) {
+        long long off = 0;
+        for (int i = 0; i < cpi; ++i) off += counts[i] < max_dets ? counts[i] : max_dets;
+        offset_sh = off;
+    }
+    __syncthreads();
+    const int n = counts[cpi] < max_dets ? counts[cpi] : max_dets;
+    const rdp_det* row = dets + (long long)cpi * max_dets;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        rdp_det d = row[i];
+        d.cpi += cpi_offset;
+        packed[offset_sh + i] = d;
+    }
+}
+
+int check_cfg(const rdp_config* c) {
+    if (!c) return fail(nullptr, RDP_E_INVALID, "config is NULL");
+    if (c->struct_size != (int32_t)sizeof(rdp_config))
+        return fail(nullptr, RDP_E_INVALID, "rdp_config.struct_size %d != %d (ABI mismatch)", c->struct_size,
+                    (int)sizeof(rdp_config));
+    if (!is_pow2(c->n_chirps) || c->n_chirps < 8 || c->n_chirps > 4096)
+        return fail(nullptr, RDP_E_INVALID, "n_chirps must be a power of two in [8, 4096], got %d", c->n_chirps);
+    if (!is_pow2(c->n_samples) || c->n_samples < 8 || c->n_samples > 4096)
+        return fail(nullptr, RDP_E_INVALID, "n_samples must be a power of two in [8, 4096], got %d", c->n_samples);
+    if (c->n_channels < 1 || c->n_channels > 65535) return fail(nullptr, RDP_E_INVALID, "n_channels out of range");
+    if (c->cfar_ref_r < 0 || c->cfar_ref_d < 0 || c->cfar_guard_r < 0 || c->cfar_guard_d < 0 ||
+        c->cfar_ref_r + c->cfar_ref_d == 0)
+        return fail(nullptr, RDP_E_INVALID, "bad CFAR extents");
+    if (c->rank_pct < 0 || c->rank_pct > 100) return fail(nullptr, RDP_E_INVALID, "rank_pct must be 0..100");
+    if (c->scale_min < 1 || c->scale_nom < 1 || c->scale_max < 1) return fail(nullptr, RDP_E_INVALID, "scales must be >= 1");
+    if (c->scale_override < 0 || c->scale_override > 7)
+        return fail(nullptr, RDP_E_INVALID, "scale_override is a 3-bit field (0..7), got %d", c->scale_override);
+    if (c->mti_mode != 0 && c->mti_mode != 2 && c->mti_mode != 3)
+        return fail(nullptr, RDP_E_INVALID, "mti_mode must be 0 (bypass), 2 or 3");
+    if (c->input_format != RDP_IN_INT16_IQ && c->input_format != RDP_IN_COMPLEX64)
+        return fail(nullptr, RDP_E_INVALID, "unknown input_format %d", c->input_format);
+    if (c->mag_mode < 0 || c->mag_mode > 3) return fail(nullptr, RDP_E_INVALID, "unknown mag_mode %d", c->mag_mode);
+    if (c->cfar_axes < 0 || c->cfar_axes > 1 || c->cfar_edges < 0 || c->cfar_edges > 1)
+        return fail(nullptr, RDP_E_INVALID, "unknown cfar_axes / cfar_edges");
+    if (c->max_dets_per_cpi < 1 || c->max_dets_per_cpi > 8192)
+        return fail(nullptr, RDP_E_INVALID, "max_dets_per_cpi must be 1..8192");
+    if (c->max_cpis < 1) return fail(nullptr, RDP_E_INVALID, "max_cpis must be >= 1");
+    if (c->chunk_cpis < 0) return fail(nullptr, RDP_E_INVALID, "chunk_cpis must be >= 0");
+    return RDP_OK;
+}
+
+void release(rdp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto& se : h->stage_events) { cudaEventDestroy(se.a); cudaEventDestroy(se.b); }
+    for (auto e : h->ev_copied) cudaEventDestroy(e);
+    for (auto e : h->ev_done) cudaEventDestroy(e);
+    for (auto e : h->ev_mapout) cudaEventDestroy(e);
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
+    void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
+                    h->in_stage[0], h->in_stage[1], h->counts, h->status, h->dets, h->packed, h->l2_flush};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    delete h;
+}
+
+int upload_tables(rdp_handle* h, int n, float gain, float** win, float2** tw) {
+    std::vector<float> w(n);
+    std::vector<float2> t(n);
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < n; ++i) {
+        // Hamming, same formula as the ROM generator (window_multiplier.vhd:41-42); the float32
+        // coefficient is formed first, then the gain, exactly as the oracle does
+        float coef = (float)(0.54 - 0.46 * std::cos(2.0 * pi * (double)i / (double)(n - 1)));
+        w[i] = (float)((double)coef * (double)gain);
+        double ang = -2.0 * pi * (double)i / (double)n;
+        t[i] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    int rc = dev_alloc(h, win, (size_t)n);
+    if (rc) return rc;
+    rc = dev_alloc(h, tw, (size_t)n);
+    if (rc) return rc;
+    RDP_CUDA(h, cudaMemcpy(*win, w.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    RDP_CUDA(h, cudaMemcpy(*tw, t.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    return RDP_OK;
+}
+
+int init_handle(rdp_handle* h) {
+    const rdp_config& c = h->cfg;
+    cudaDeviceProp prop;
+    RDP_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    RDP_CUDA(h, cudaEventCreate(&h->t0));
+    RDP_CUDA(h, cudaEventCreate(&h->t1));
+
+    int rc = upload_tables(h, c.n_samples, c.window_gain, &h->win_r, &h->tw_r);
+    if (rc) return rc;
+    rc = upload_tables(h, c.n_chirps, c.window_gain, &h->win_d, &h->tw_d);
+    if (rc) return rc;
+
+    // kernels
+    bool ok = (c.input_format == RDP_IN_INT16_IQ) ? k1_for<0>(c.n_samples, &h->k1) : k1_for<1>(c.n_samples, &h->k1);
+    if (!ok) return fail(h, RDP_E_INVALID, "no range-FFT plan for n_samples=%d", c.n_samples);
+    switch (c.mag_mode) {
+        case 0: ok = k2_for<0>(c.n_chirps, &h->k2); break;
+        case 1: ok = k2_for<1>(c.n_chirps, &h->k2); break;
+        case 2: ok = k2_for<2>(c.n_chirps, &h->k2); break;
+        default: ok = k2_for<3>(c.n_chirps, &h->k2); break;
+    }
+    if (!ok) return fail(h, RDP_E_INVALID, "no Doppler-FFT plan for n_chirps=%d", c.n_chirps);
+    h->k1_tile_chirps = h->k1.tc_max < c.n_chirps ? h->k1.tc_max : c.n_chirps;
+    h->k1_smem = h->k1.smem(h->k1_tile_chirps);
+    int occ = 1;
+    RDP_CUDA(h, h->k1.prepare(h->k1_smem, &occ));
+    h->k1_grid_cap = h->sm_count * occ;
+    RDP_CUDA(h, h->k2.prepare(h->k2.smem, &occ));
+    h->k2_grid_cap = h->sm_count * occ;
+
+    // CFAR geometry in physical axes (os_cfar_2d.vhd:41-47)
+    CfarArgs& a = h->cfar;
+    a.n_range = c.n_samples; a.n_doppler = c.n_chirps; a.n_channels = c.n_channels;
+    if (c.cfar_axes == RDP_AXES_AS_BUILT) {
+        a.half_l = c.cfar_ref_d + c.cfar_guard_d; a.guard_l = c.cfar_guard_d;
+        a.half_c = c.cfar_ref_r + c.cfar_guard_r; a.guard_c = c.cfar_guard_r;
+    } else {
+        a.half_l = c.cfar_ref_r + c.cfar_guard_r; a.guard_l = c.cfar_guard_r;
+        a.half_c = c.cfar_ref_d + c.cfar_guard_d; a.guard_c = c.cfar_guard_d;
+    }
+    const int win = (2 * a.half_l + 1) * (2 * a.half_c + 1);
+    a.n_ref = win - (2 * a.guard_l + 1) * (2 * a.guard_c + 1);
+    if (a.n_ref < 1) return fail(h, RDP_E_INVALID, "CFAR window has no reference cells");
+    if (win > 32 * MAXQ_GENERIC) return fail(h, RDP_E_INVALID, "CFAR window of %d cells exceeds %d", win, 32 * MAXQ_GENERIC);
+    a.rank_idx = (a.n_ref * c.rank_pct) / 100;                    // os_cfar_2d.vhd:181-182
+    if (a.rank_idx >= a.n_ref) a.rank_idx = a.n_ref - 1;
+    a.smin = (float)c.scale_min; a.snom = (float)c.scale_nom; a.smax = (float)c.scale_max;
+    a.adaptive = c.scale_override == 0;
+    if (a.adaptive) {
+        int s1 = c.scale_min < c.scale_nom ? c.scale_min : c.scale_nom;
+        if (c.scale_max < s1) s1 = c.scale_max;
+        a.s1 = (float)s1;
+    } else {
+        a.s1 = (float)c.scale_override;
+    }
+    a.raster = c.cfar_edges == RDP_EDGES_RASTER;
+    a.max_dets = c.max_dets_per_cpi;
+    h->k3 = k3_for(a.half_l, a.half_c, a.guard_l, a.guard_c);
+    RDP_CUDA(h, h->k3.prepare(h->k3.smem));
+    h->sort_pow2 = 2;
+    while (h->sort_pow2 < c.max_dets_per_cpi) h->sort_pow2 <<= 1;
+    {
+        size_t smem = (size_t)h->sort_pow2 * (sizeof(unsigned long long) + sizeof(float));
+        RDP_CUDA(h, prepare_kernel(k4_sort_dets_kernel, 256, smem, nullptr));
+    }
+
+    // chunking: keep the range-major intermediate of one chunk L2-resident between K1 and K2
+    const size_t xrc_per_cpi = cells_per_cpi(c) * sizeof(float2);
+    int chunk = c.chunk_cpis;
+    if (chunk == 0) {
+        size_t l2 = (size_t)prop.l2CacheSize;
+        size_t budget = l2 / 2;
+        chunk = (int)(budget / xrc_per_cpi);
+        if (chunk < 1) chunk = 1;
+    }
+    if (chunk > c.max_cpis) chunk = c.max_cpis;
+    h->chunk = chunk;
+    rc = dev_alloc(h, &h->x_rc, (size_t)chunk * cells_per_cpi(c));
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i) {
+        rc = dev_alloc(h, &h->map_scratch[i], (size_t)chunk * cells_per_cpi(c));
+        if (rc) return rc;
+    }
+    rc = dev_alloc(h, &h->counts, (size_t)c.max_cpis);
+    if (rc) return rc;
+    rc = dev_alloc(h, &h->status, (size_t)c.max_cpis);
+    if (rc) return rc;
+    return RDP_OK;
+}
+
+int ensure_host_path(rdp_handle* h) {
+    const rdp_config& c = h->cfg;
+    if (h->in_stage[0]) return RDP_OK;
+    for (int i = 0; i < 2; ++i) {
+        unsigned char* p = nullptr;
+        int rc = dev_alloc(h, &p, (size_t)h->chunk * cells_per_cpi(c) * in_bytes_per_sample(c));
+        if (rc) return rc;
+        h->in_stage[i] = p;
+    }
+    int rc = dev_alloc(h, &h->dets, (size_t)c.max_cpis * c.max_dets_per_cpi);
+    if (rc) return rc;
+    rc = dev_alloc(h, &h->packed, (size_t)c.max_cpis * c.max_dets_per_cpi);
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        RDP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDefault)); h->ev_copied.push_back(e);
+        RDP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDefault)); h->ev_done.push_back(e);
+        RDP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDefault)); h->ev_mapout.push_back(e);
+    }
+    return RDP_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+#ifdef RDP_EMU
+int rdp_emu_marker(void) { return 1; }   // the product loader refuses libraries exporting this
+#endif
+
+void rdp_default_config(rdp_config* cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (int32_t)sizeof(rdp_config);
+    cfg->n_chirps = 128;          // N_DOPPLER  radar_core.vhd:14
+    cfg->n_samples = 1024;        // N_RANGE    radar_core.vhd:13
+    cfg->n_channels = 1;
+    cfg->cfar_ref_r = 4; cfg->cfar_ref_d = 4; cfg->cfar_guard_r = 2; cfg->cfar_guard_d = 1;   // :16-19
+    cfg->rank_pct = 75; cfg->scale_min = 2; cfg->scale_nom = 4; cfg->scale_max = 6;           // :380
+    cfg->scale_override = 0;
+    cfg->mti_mode = 0;
+    cfg->input_format = RDP_IN_INT16_IQ;
+    cfg->mag_mode = RDP_MAG_AMB;
+    cfg->cfar_axes = RDP_AXES_AS_BUILT;
+    cfg->cfar_edges = RDP_EDGES_ZERO;
+    cfg->window_gain = 1.0f;
+    cfg->max_dets_per_cpi = 4096;
+    cfg->max_cpis = 1;
+    cfg->chunk_cpis = 0;
+}
+
+int rdp_create(const rdp_config* cfg, int32_t device, rdp_handle** out) {
+    if (!out) return fail(nullptr, RDP_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev < 1)
+        return fail(nullptr, RDP_E_NO_DEVICE, "no CUDA device available (%s); librdp has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n_dev) return fail(nullptr, RDP_E_NO_DEVICE, "device %d out of range [0, %d)", device, n_dev);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, RDP_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    rdp_handle* h = new (std::nothrow) rdp_handle();
+    if (!h) return fail(nullptr, RDP_E_NOMEM, "out of host memory");
+    h->cfg = *cfg;
+    h->device = device;
+    rc = init_handle(h);
+    if (rc) {
+        g_create_error = h->err;
+        release(h);
+        return rc;
+    }
+    *out = h;
+    return RDP_OK;
+}
+
+int rdp_destroy(rdp_handle* h) {
+    if (!h) return RDP_E_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    release(h);
+    return RDP_OK;
+}
+
+const char* rdp_last_error(const rdp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rdp_get_info(const rdp_handle* h, rdp_info* info) {
+    if (!h || !info) return RDP_E_INVALID;
+    std::memset(info, 0, sizeof(*info));
+    info->abi_version = RDP_ABI_VERSION;
+    info->device = h->device;
+    info->sm_count = h->sm_count;
+    info->chunk_cpis = h->chunk;
+    info->scratch_bytes = h->scratch_bytes;
+    info->kernel_launches = h->launches;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess)
+        std::snprintf(info->device_name, sizeof(info->device_name), "%s", prop.name);
+    return RDP_OK;
+}
+
+int rdp_sync(rdp_handle* h) {
+    if (!h) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RDP_OK;
+}
+
+int rdp_range_stage(rdp_handle* h, const void* cube, int32_t n_cpi, void* x_rc) {
+    if (!h || !cube || !x_rc || n_cpi < 0) return fail(h, RDP_E_INVALID, "rdp_range_stage: bad argument");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    return run_range(h, cube, n_cpi, reinterpret_cast<float2*>(x_rc));
+}
+
+int rdp_doppler_stage(rdp_handle* h, const void* x_rc, int32_t n_cpi, float* rd_map) {
+    if (!h || !x_rc || !rd_map || n_cpi < 0) return fail(h, RDP_E_INVALID, "rdp_doppler_stage: bad argument");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    return run_doppler(h, reinterpret_cast<const float2*>(x_rc), n_cpi, rd_map);
+}
+
+int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfar_out, rdp_det* dets,
+                   int32_t* n_dets, uint32_t* status) {
+    if (!h || !rd_map || !dets || !n_dets || !status || n_cpi < 0)
+        return fail(h, RDP_E_INVALID, "rdp_cfar_stage: bad argument");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaMemsetAsync(n_dets, 0, sizeof(int32_t) * (size_t)n_cpi, h->stream));
+    int rc = run_cfar(h, rd_map, n_cpi, cfar_out, dets, n_dets);
+    if (rc) return rc;
+    return run_sort(h, dets, n_dets, status, n_cpi);
+}
+
+int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map, rdp_det* dets,
+                       int32_t* n_dets, uint32_t* status) {
+    if (!h || !cube || !dets || !n_dets || !status || n_cpi < 0)
+        return fail(h, RDP_E_INVALID, "rdp_process_device: bad argument");
+    const rdp_config& c = h->cfg;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaMemsetAsync(n_dets, 0, sizeof(int32_t) * (size_t)n_cpi, h->stream));
+    const size_t cells = cells_per_cpi(c);
+    const size_t in_stride = cells * in_bytes_per_sample(c);
+    for (int base = 0; base < n_cpi; base += h->chunk) {
+        const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
+        const unsigned char* in = reinterpret_cast<const unsigned char*>(cube) + (size_t)base * in_stride;
+        float* map = rd_map ? rd_map + (size_t)base * cells : h->map_scratch[0];
+        int rc = run_range(h, in, n, h->x_rc);
+        if (rc) return rc;
+        rc = run_doppler(h, h->x_rc, n, map);
+        if (rc) return rc;
+        // records carry the CPI index relative to this chunk's counts/dets pointers; fix below
+        rc = run_cfar(h, map, n, nullptr, dets + (size_t)base * c.max_dets_per_cpi, n_dets + base);
+        if (rc) return rc;
+    }
+    return run_sort(h, dets, n_dets, status, n_cpi);
+}
+
+int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map, rdp_det* dets,
+                     int32_t* n_dets, uint32_t* status) {
+    if (!h || !cube || !dets || !n_dets || !status || n_cpi < 0)
+        return fail(h, RDP_E_INVALID, "rdp_process_host: bad argument");
+    const rdp_config& c = h->cfg;
+    if (n_cpi > c.max_cpis) return fail(h, RDP_E_CAPACITY, "n_cpi %d exceeds max_cpis %d", n_cpi, c.max_cpis);
+    if (n_cpi == 0) return RDP_OK;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_host_path(h);
+    if (rc) return rc;
+    const size_t cells = cells_per_cpi(c);
+    const size_t in_stride = cells * in_bytes_per_sample(c);
+    RDP_CUDA(h, cudaMemsetAsync(h->counts, 0, sizeof(int) * (size_t)n_cpi, h->stream));
+    int k = 0;
+    for (int base = 0; base < n_cpi; base += h->chunk, ++k) {
+        const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
+        const int b = k & 1;
+        // H2D of chunk k on the copy stream, once the kernels that read this staging buffer (chunk k-2) are done
+        if (k >= 2) RDP_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));
+        RDP_CUDA(h, cudaMemcpyAsync(h->in_stage[b], reinterpret_cast<const unsigned char*>(cube) + (size_t)base * in_stride,
+                                    (size_t)n * in_stride, cudaMemcpyHostToDevice, h->copy_stream));
+        RDP_CUDA(h, cudaEventRecord(h->ev_copied[b], h->copy_stream));
+        RDP_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
+        if (rd_map && k >= 2) RDP_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_mapout[b], 0));
+        float* map = h->map_scratch[b];
+        rc = run_range(h, h->in_stage[b], n, h->x_rc);
+        if (rc) return rc;
+        rc = run_doppler(h, h->x_rc, n, map);
+        if (rc) return rc;
+        rc = run_cfar(h, map, n, nullptr, h->dets + (size_t)base * c.max_dets_per_cpi, h->counts + base);
+        if (rc) return rc;
+        RDP_CUDA(h, cudaEventRecord(h->ev_done[b], h->stream));
+        if (rd_map) {
+            RDP_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_done[b], 0));
+            RDP_CUDA(h, cudaMemcpyAsync(rd_map + (size_t)base * cells, map, (size_t)n * cells * sizeof(float),
+                                        cudaMemcpyDeviceToHost, h->d2h_stream));
+            RDP_CUDA(h, cudaEventRecord(h->ev_mapout[b], h->d2h_stream));
+        }
+    }
+    rc = run_sort(h, h->dets, h->counts, h->status, n_cpi);
+    if (rc) return rc;
+    h->launches += 1;
+    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, h->dets, h->counts, h->packed, c.max_dets_per_cpi, 0);
+    rc = launch_check(h, "k5_pack_dets_kernel");
+    if (rc) return rc;
+    RDP_CUDA(h, cudaMemcpyAsync(n_dets, h->counts, sizeof(int) * (size_t)n_cpi, cudaMemcpyDeviceToHost, h->stream));
+    RDP_CUDA(h, cudaMemcpyAsync(status, h->status, sizeof(uint32_t) * (size_t)n_cpi, cudaMemcpyDeviceToHost, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    long long total = 0;
+    for (int i = 0; i < n_cpi; ++i) total += n_dets[i] < c.max_dets_per_cpi ? n_dets[i] : c.max_dets_per_cpi;
+    if (total > 0)
+        RDP_CUDA(h, cudaMemcpyAsync(dets, h->packed, sizeof(rdp_det) * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (rd_map) RDP_CUDA(h, cudaStreamSynchronize(h->d2h_stream));
+    return RDP_OK;
+}
+
+int rdp_device_alloc(rdp_handle* h, size_t bytes, void** ptr) {
+    if (!h || !ptr) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaMalloc(ptr, bytes ? bytes : 16));
+    return RDP_OK;
+}
+int rdp_device_free(rdp_handle* h, void* ptr) {
+    if (!h) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaFree(ptr));
+    return RDP_OK;
+}
+int rdp_host_alloc(rdp_handle* h, size_t bytes, void** ptr) {
+    if (!h || !ptr) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return RDP_OK;
+}
+int rdp_host_free(rdp_handle* h, void* ptr) {
+    if (!h) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaFreeHost(ptr));
+    return RDP_OK;
+}
+int rdp_copy_h2d(rdp_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!h || (!dst && bytes) || (!src && bytes)) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RDP_OK;
+}
+int rdp_copy_d2h(rdp_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!h || (!dst && bytes) || (!src && bytes)) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RDP_OK;
+}
+
+int rdp_timer_start(rdp_handle* h) {
+    if (!h) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaEventRecord(h->t0, h->stream));
+    return RDP_OK;
+}
+int rdp_timer_stop(rdp_handle* h, float* elapsed_ms) {
+    if (!h || !elapsed_ms) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaEventRecord(h->t1, h->stream));
+    RDP_CUDA(h, cudaEventSynchronize(h->t1));
+    RDP_CUDA(h, cudaEventElapsedTime(elapsed_ms, h->t0, h->t1));
+    return RDP_OK;
+}
+int rdp_set_stage_timing(rdp_handle* h, int32_t enable) {
+    if (!h) return RDP_E_INVALID;
+    h->stage_timing = enable != 0;
+    return RDP_OK;
+}
+int rdp_get_stage_timing(rdp_handle* h, float ms[4], int64_t launches[4]) {
+    if (!h || !ms || !launches) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (auto& se : h->stage_events) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, se.a, se.b) == cudaSuccess) h->stage_ms[se.stage] += t;
+        cudaEventDestroy(se.a);
+        cudaEventDestroy(se.b);
+    }
+    h->stage_events.clear();
+    for (int i = 0; i < 4; ++i) {
+        ms[i] = h->stage_ms[i];
+        launches[i] = h->stage_launches[i];
+        h->stage_ms[i] = 0.f;
+        h->stage_launches[i] = 0;
+    }
+    return RDP_OK;
+}
+int rdp_flush_l2(rdp_handle* h) {
+    if (!h) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    if (!h->l2_flush) {
+        cudaDeviceProp prop;
+        RDP_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+        h->l2_flush_bytes = (size_t)prop.l2CacheSize * 2 + (64u << 20);
+        RDP_CUDA(h, cudaMalloc(&h->l2_flush, h->l2_flush_bytes));
+    }
+    RDP_CUDA(h, cudaMemsetAsync(h->l2_flush, 0x5a, h->l2_flush_bytes, h->stream));
+    return RDP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+"""The reference's detection text format: one `range_bin doppler_bin magnitude` line per
+detection, decimal integers (writer: rtl/src/tb_radar_core.vhd:149-160; reader:
+model/ADR_visualize.py:109-122).  Files written here can be fed to the reference's plotters."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def write_detections(path, dets, cpi=None, channel=None) -> int:
+    """Write `r d mag` lines for the detections of one (cpi, channel) (all if None).
+    Magnitudes are rounded to integers as the RTL's 17-bit word would be.  Returns the line count."""
+    sel = np.ones(len(dets), dtype=bool)
+    if cpi is not None:
+        sel &= dets["cpi"] == cpi
+    if channel is not None:
+        sel &= dets["channel"] == channel
+    d = dets[sel]
+    with open(path, "w") as f:
+        for r, c, m in zip(d["range"], d["doppler"], d["mag"]):
+            f.write(f"{int(r)} {int(c)} {int(round(float(m)))}\n")
+    return int(sel.sum())
+
+
+def read_detections(path) -> np.ndarray:
+    """Parse `r d mag` lines the way model/ADR_visualize.py:109-122 does (3 integers, others skipped)."""
+    rows = []
+    with open(path) as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) != 3:
+                continue
+            try:
+                rows.append(tuple(int(p) for p in parts))
+            except ValueError:
+                continue
+    return np.asarray(rows, dtype=np.int64).reshape(-1, 3)

@@ -1,0 +1,392 @@
+"""Python host side of the B200 range-Doppler + OS-CFAR path (ctypes over include/rdp.h).
+
+The reference (Aurellia-Beam/fpga-fmcw-radar-processor) has no software API; its interface
+for this path is the `radar_core` entity -- generics, ADC stream in, detection stream out,
+two control pins (rtl/src/radar_core.vhd:11-57) -- and the `r d mag` text records its
+testbenches write (rtl/src/tb_radar_core.vhd:149-160).  `RadarCore` mirrors that entity:
+constructor arguments are the generics / pins under their RTL names, `process()` is one or
+more CPIs in, range-Doppler map + detection list out.
+
+No PyTorch, no cuFFT, no CPU fallback: everything numeric happens in librdp.so's sm_100a
+kernels; if the library or a GPU is missing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIBRARY = os.path.join(_HERE, "librdp.so")
+
+RDP_OK = 0
+ERRORS = {-1: "RDP_E_INVALID", -2: "RDP_E_NO_DEVICE", -3: "RDP_E_CUDA", -4: "RDP_E_NOMEM", -5: "RDP_E_CAPACITY"}
+STATUS_DET_OVERFLOW = 1
+
+INPUT_FORMATS = {"int16": 0, "complex64": 1}
+MAG_MODES = {"amb": 0, "abs": 1, "pow": 2, "logpow": 3}
+CFAR_AXES = {"as_built": 0, "as_named": 1}
+CFAR_EDGES = {"zero": 0, "raster": 1}
+
+# one `r d mag` record (+ CPI, channel); layout == struct rdp_det
+DET_DTYPE = np.dtype([("cpi", "<i4"), ("channel", "<i4"), ("range", "<i4"), ("doppler", "<i4"), ("mag", "<f4")])
+
+
+class RdpError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"{ERRORS.get(code, code)}: {message}")
+        self.code = code
+
+
+class RdpConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "struct_size", "n_chirps", "n_samples", "n_channels", "cfar_ref_r", "cfar_ref_d", "cfar_guard_r",
+        "cfar_guard_d", "rank_pct", "scale_min", "scale_nom", "scale_max", "scale_override", "mti_mode",
+        "input_format", "mag_mode", "cfar_axes", "cfar_edges")] + [("window_gain", C.c_float)] + [
+        (n, C.c_int32) for n in ("max_dets_per_cpi", "max_cpis", "chunk_cpis")]
+
+
+class RdpInfo(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("sm_count", C.c_int32),
+                ("chunk_cpis", C.c_int32), ("scratch_bytes", C.c_int64), ("kernel_launches", C.c_int64),
+                ("device_name", C.c_char * 128)]
+
+
+# every symbol include/rdp.h declares: name -> (restype, argtypes)
+_VP, _I32, _SZ = C.c_void_p, C.c_int32, C.c_size_t
+SYMBOLS = {
+    "rdp_default_config": (None, [C.POINTER(RdpConfig)]),
+    "rdp_create": (C.c_int, [C.POINTER(RdpConfig), _I32, C.POINTER(_VP)]),
+    "rdp_destroy": (C.c_int, [_VP]),
+    "rdp_last_error": (C.c_char_p, [_VP]),
+    "rdp_get_info": (C.c_int, [_VP, C.POINTER(RdpInfo)]),
+    "rdp_process_device": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "rdp_process_host": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "rdp_sync": (C.c_int, [_VP]),
+    "rdp_range_stage": (C.c_int, [_VP, _VP, _I32, _VP]),
+    "rdp_doppler_stage": (C.c_int, [_VP, _VP, _I32, _VP]),
+    "rdp_cfar_stage": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "rdp_device_alloc": (C.c_int, [_VP, _SZ, C.POINTER(_VP)]),
+    "rdp_device_free": (C.c_int, [_VP, _VP]),
+    "rdp_host_alloc": (C.c_int, [_VP, _SZ, C.POINTER(_VP)]),
+    "rdp_host_free": (C.c_int, [_VP, _VP]),
+    "rdp_copy_h2d": (C.c_int, [_VP, _VP, _VP, _SZ]),
+    "rdp_copy_d2h": (C.c_int, [_VP, _VP, _VP, _SZ]),
+    "rdp_timer_start": (C.c_int, [_VP]),
+    "rdp_timer_stop": (C.c_int, [_VP, C.POINTER(C.c_float)]),
+    "rdp_set_stage_timing": (C.c_int, [_VP, _I32]),
+    "rdp_get_stage_timing": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "rdp_flush_l2": (C.c_int, [_VP]),
+}
+
+_LIB_CACHE = {}
+
+
+def load_library(path: str | None = None, _test_allow_emulator: bool = False):
+    """dlopen librdp.so and bind every symbol of include/rdp.h.  Fails loudly when the
+    library has not been built (python __graft_entry__.py / make -C <package>)."""
+    path = os.path.abspath(path or DEFAULT_LIBRARY)
+    key = (path, _test_allow_emulator)
+    if key in _LIB_CACHE:
+        return _LIB_CACHE[key]
+    if not os.path.exists(path):
+        raise RdpError(-3, f"{path} not found: build the CUDA library first "
+                           f"(`python __graft_entry__.py` or `make -C {_HERE}`); there is no CPU fallback")
+    lib = C.CDLL(path)
+    if hasattr(lib, "rdp_emu_marker") and not _test_allow_emulator:
+        raise RdpError(-3, f"{path} is the host-emulation test harness, not the CUDA library; refusing to use it")
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError here = library / header drift
+        fn.restype, fn.argtypes = res, args
+    _LIB_CACHE[key] = lib
+    return lib
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class DeviceBuffer:
+    """Caller-owned device memory (rdp_device_alloc)."""
+
+    def __init__(self, core: "RadarCore", nbytes: int):
+        self.core, self.nbytes = core, int(nbytes)
+        p = C.c_void_p()
+        core._check(core.lib.rdp_device_alloc(core.h, self.nbytes, C.byref(p)))
+        self.ptr = p
+
+    def upload(self, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        self.core._check(self.core.lib.rdp_copy_h2d(self.core.h, self.ptr, _ptr(a), a.nbytes))
+        return self
+
+    def download(self, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        self.core._check(self.core.lib.rdp_copy_d2h(self.core.h, _ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr is not None and self.core.h:
+            self.core.lib.rdp_device_free(self.core.h, self.ptr)
+        self.ptr = None
+
+
+class RadarCore:
+    """The `radar_core` entity (rtl/src/radar_core.vhd:11-57) on one B200.
+
+    Generics keep their RTL names (n_range = N_RANGE = samples per chirp, n_doppler =
+    N_DOPPLER = chirps per CPI, cfar_ref_r ... cfar_guard_d), `mti_mode=0` is the
+    `mti_bypass` pin, `scale_override` the `cfar_scale_ovr` pin.
+    """
+
+    def __init__(self, n_range=1024, n_doppler=128, n_channels=1, cfar_ref_r=4, cfar_ref_d=4,
+                 cfar_guard_r=2, cfar_guard_d=1, rank_pct=75, scale_min=2, scale_nom=4, scale_max=6,
+                 scale_override=0, mti_mode=0, input_format="int16", mag_mode="amb",
+                 cfar_axes="as_built", cfar_edges="zero", window_gain=1.0, max_dets_per_cpi=4096,
+                 max_cpis=1, chunk_cpis=0, device=0, library=None, _test_allow_emulator=False):
+        self.lib = load_library(library, _test_allow_emulator)
+        cfg = RdpConfig()
+        self.lib.rdp_default_config(C.byref(cfg))
+        cfg.n_samples, cfg.n_chirps, cfg.n_channels = n_range, n_doppler, n_channels
+        cfg.cfar_ref_r, cfg.cfar_ref_d, cfg.cfar_guard_r, cfg.cfar_guard_d = cfar_ref_r, cfar_ref_d, cfar_guard_r, cfar_guard_d
+        cfg.rank_pct, cfg.scale_min, cfg.scale_nom, cfg.scale_max = rank_pct, scale_min, scale_nom, scale_max
+        cfg.scale_override, cfg.mti_mode = scale_override, mti_mode
+        try:
+            cfg.input_format = INPUT_FORMATS[input_format]
+            cfg.mag_mode = MAG_MODES[mag_mode]
+            cfg.cfar_axes = CFAR_AXES[cfar_axes]
+            cfg.cfar_edges = CFAR_EDGES[cfar_edges]
+        except KeyError as e:
+            raise RdpError(-1, f"unknown option {e}") from None
+        cfg.window_gain = window_gain
+        cfg.max_dets_per_cpi, cfg.max_cpis, cfg.chunk_cpis = max_dets_per_cpi, max_cpis, chunk_cpis
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.lib.rdp_create(C.byref(cfg), device, C.byref(self.h))
+        if rc != RDP_OK:
+            self.h = C.c_void_p()
+            raise RdpError(rc, (self.lib.rdp_last_error(None) or b"").decode())
+        self.n_range, self.n_doppler, self.n_channels = n_range, n_doppler, n_channels
+        self.input_format = input_format
+        self.max_dets_per_cpi, self.max_cpis = max_dets_per_cpi, max_cpis
+        self._pinned = []
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != RDP_OK:
+            raise RdpError(rc, (self.lib.rdp_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            for p in self._pinned:
+                self.lib.rdp_host_free(self.h, p)
+            self._pinned = []
+            self.lib.rdp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        i = RdpInfo()
+        self._check(self.lib.rdp_get_info(self.h, C.byref(i)))
+        return dict(abi_version=i.abi_version, device=i.device, sm_count=i.sm_count, chunk_cpis=i.chunk_cpis,
+                    scratch_bytes=i.scratch_bytes, kernel_launches=i.kernel_launches,
+                    device_name=i.device_name.decode())
+
+    def sync(self):
+        self._check(self.lib.rdp_sync(self.h))
+
+    def device_buffer(self, nbytes) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array backed by page-locked host memory (rdp_host_alloc); freed by close()."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self.lib.rdp_host_alloc(self.h, max(n, 16), C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_ubyte * max(n, 16)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    # -- shapes -----------------------------------------------------------------------------
+    @property
+    def cells_per_cpi(self) -> int:
+        return self.n_channels * self.n_range * self.n_doppler
+
+    @property
+    def in_bytes_per_cpi(self) -> int:
+        return self.cells_per_cpi * (4 if self.input_format == "int16" else 8)
+
+    def _as_cube(self, cube: np.ndarray) -> np.ndarray:
+        """-> C-contiguous [cpi, channel, chirp, sample(, 2)] of int16 / complex64."""
+        cube = np.asarray(cube)
+        if self.input_format == "int16":
+            if cube.dtype != np.int16 or cube.shape[-1] != 2:
+                raise RdpError(-1, "int16 input must be int16 [..., chirp, sample, 2] = (I, Q)")
+            core = cube.shape[:-1]
+        else:
+            if cube.dtype != np.complex64:
+                raise RdpError(-1, "complex64 input must be complex64 [..., chirp, sample]")
+            core = cube.shape
+        if core[-2:] != (self.n_doppler, self.n_range):
+            raise RdpError(-1, f"frame must be [{self.n_doppler} chirps, {self.n_range} samples], got {core[-2:]}")
+        lead = core[:-2]
+        if len(lead) == 0:
+            lead = (1, 1)
+        elif len(lead) == 1:
+            lead = (1, lead[0])
+        elif len(lead) != 2:
+            raise RdpError(-1, "input must be [chirp, sample], [channel, ...] or [cpi, channel, ...]")
+        if lead[1] != self.n_channels:
+            raise RdpError(-1, f"expected {self.n_channels} channels, got {lead[1]}")
+        tail = (self.n_doppler, self.n_range) + ((2,) if self.input_format == "int16" else ())
+        return np.ascontiguousarray(cube).reshape(lead + tail)
+
+    # -- the path ---------------------------------------------------------------------------
+    def process(self, cube: np.ndarray, want_map: bool = True):
+        """HOST buffers in, HOST results out (rdp_process_host).
+        Returns (rd_map float32 [cpi, channel, range, doppler] or None,
+                 detections DET_DTYPE in canonical (cpi, channel, range, doppler) order,
+                 n_dets int32 [cpi] (as found; > max_dets_per_cpi means truncated), status uint32 [cpi])."""
+        cube = self._as_cube(cube)
+        n_cpi = cube.shape[0]
+        rd_map = np.empty((n_cpi, self.n_channels, self.n_range, self.n_doppler), np.float32) if want_map else None
+        dets = np.empty(n_cpi * self.max_dets_per_cpi, dtype=DET_DTYPE)
+        n_dets = np.zeros(n_cpi, np.int32)
+        status = np.zeros(n_cpi, np.uint32)
+        self._check(self.lib.rdp_process_host(self.h, _ptr(cube), n_cpi, _ptr(rd_map) if want_map else None,
+                                              _ptr(dets), _ptr(n_dets), _ptr(status)))
+        total = int(np.minimum(n_dets, self.max_dets_per_cpi).sum())
+        return rd_map, dets[:total].copy(), n_dets, status
+
+    def process_device(self, d_cube: DeviceBuffer, n_cpi: int, d_map: DeviceBuffer | None,
+                       d_dets: DeviceBuffer, d_counts: DeviceBuffer, d_status: DeviceBuffer):
+        """DEVICE buffers in and out, asynchronous (rdp_process_device)."""
+        self._check(self.lib.rdp_process_device(self.h, d_cube.ptr, n_cpi, d_map.ptr if d_map else None,
+                                                d_dets.ptr, d_counts.ptr, d_status.ptr))
+
+    def unpack_device_dets(self, d_dets: DeviceBuffer, d_counts: DeviceBuffer, n_cpi: int):
+        counts = d_counts.download((n_cpi,), np.int32)
+        rows = d_dets.download((n_cpi, self.max_dets_per_cpi), DET_DTYPE)
+        keep = [rows[i, :min(int(counts[i]), self.max_dets_per_cpi)] for i in range(n_cpi)]
+        return (np.concatenate(keep) if keep else np.zeros(0, DET_DTYPE)), counts
+
+    # -- stage taps (device work, host arrays in/out; for parity tests) -----------------------
+    def range_stage(self, cube: np.ndarray) -> np.ndarray:
+        cube = self._as_cube(cube)
+        n_cpi = cube.shape[0]
+        d_in = self.device_buffer(cube.nbytes).upload(cube)
+        d_out = self.device_buffer(n_cpi * self.cells_per_cpi * 8)
+        try:
+            self._check(self.lib.rdp_range_stage(self.h, d_in.ptr, n_cpi, d_out.ptr))
+            self.sync()
+            return d_out.download((n_cpi, self.n_channels, self.n_range, self.n_doppler), np.complex64)
+        finally:
+            d_in.free(); d_out.free()
+
+    def doppler_stage(self, x_rc: np.ndarray) -> np.ndarray:
+        x_rc = np.ascontiguousarray(x_rc, dtype=np.complex64).reshape(-1, self.n_channels, self.n_range, self.n_doppler)
+        n_cpi = x_rc.shape[0]
+        d_in = self.device_buffer(x_rc.nbytes).upload(x_rc)
+        d_out = self.device_buffer(n_cpi * self.cells_per_cpi * 4)
+        try:
+            self._check(self.lib.rdp_doppler_stage(self.h, d_in.ptr, n_cpi, d_out.ptr))
+            self.sync()
+            return d_out.download(x_rc.shape, np.float32)
+        finally:
+            d_in.free(); d_out.free()
+
+    def cfar_stage(self, rd_map: np.ndarray, want_dense: bool = True):
+        """-> (detections, n_dets, status, cfar_out or None); cfar_out is the RTL's dense output
+        word per cell (CUT magnitude or 0)."""
+        rd_map = np.ascontiguousarray(rd_map, dtype=np.float32).reshape(-1, self.n_channels, self.n_range, self.n_doppler)
+        n_cpi = rd_map.shape[0]
+        d_map = self.device_buffer(rd_map.nbytes).upload(rd_map)
+        d_dense = self.device_buffer(rd_map.nbytes) if want_dense else None
+        d_dets = self.device_buffer(n_cpi * self.max_dets_per_cpi * DET_DTYPE.itemsize)
+        d_counts = self.device_buffer(n_cpi * 4)
+        d_status = self.device_buffer(n_cpi * 4)
+        try:
+            self._check(self.lib.rdp_cfar_stage(self.h, d_map.ptr, n_cpi, d_dense.ptr if want_dense else None,
+                                                d_dets.ptr, d_counts.ptr, d_status.ptr))
+            self.sync()
+            dets, counts = self.unpack_device_dets(d_dets, d_counts, n_cpi)
+            status = d_status.download((n_cpi,), np.uint32)
+            dense = d_dense.download(rd_map.shape, np.float32) if want_dense else None
+            return dets, counts, status, dense
+        finally:
+            for b in (d_map, d_dense, d_dets, d_counts, d_status):
+                if b is not None:
+                    b.free()
+
+    # -- measurement ------------------------------------------------------------------------
+    def timer_start(self):
+        self._check(self.lib.rdp_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.rdp_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def set_stage_timing(self, on: bool):
+        self._check(self.lib.rdp_set_stage_timing(self.h, 1 if on else 0))
+
+    def stage_timing(self):
+        ms = (C.c_float * 4)()
+        n = (C.c_int64 * 4)()
+        self._check(self.lib.rdp_get_stage_timing(self.h, ms, n))
+        names = ("range", "doppler", "cfar", "sort")
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
+
+    def flush_l2(self):
+        self._check(self.lib.rdp_flush_l2(self.h))
+
+
+# ------------------------------------------------------------------------------------------------
+# Frame-in / map + detection-list-out functions, same signatures as oracle.float_path
+# ------------------------------------------------------------------------------------------------
+def _core_for(cubes: np.ndarray, n_cpi_axis: bool, kw: dict) -> RadarCore:
+    cubes = np.asarray(cubes)
+    cplx = np.iscomplexobj(cubes)
+    core_shape = cubes.shape if cplx else cubes.shape[:-1]
+    n_doppler, n_range = core_shape[-2], core_shape[-1]
+    lead = core_shape[:-2]
+    n_channels = lead[-1] if len(lead) >= 1 else 1
+    n_cpi = lead[0] if (n_cpi_axis and len(lead) == 2) else 1
+    return RadarCore(n_range=n_range, n_doppler=n_doppler, n_channels=n_channels,
+                     input_format="complex64" if cplx else "int16", max_cpis=max(1, n_cpi), **kw)
+
+
+def process_cpi(frame: np.ndarray, **kw):
+    """One CPI: frame [chirp, sample(,2)] or [channel, chirp, sample(,2)] -> (rd_map float32
+    [channel, range, doppler], detections sorted by (channel, range, doppler))."""
+    frame = np.asarray(frame)
+    if np.iscomplexobj(frame):
+        frame = frame.astype(np.complex64, copy=False)
+    with _core_for(frame, False, kw) as core:
+        m, dets, _, _ = core.process(frame)
+    return m[0], dets
+
+
+def process_batch(cubes: np.ndarray, **kw):
+    """[cpi, channel, chirp, sample(,2)] -> (maps, detections for all CPIs, per-CPI counts)."""
+    cubes = np.asarray(cubes)
+    if np.iscomplexobj(cubes):
+        cubes = cubes.astype(np.complex64, copy=False)
+    with _core_for(cubes, True, kw) as core:
+        m, dets, counts, _ = core.process(cubes)
+    return m, dets, counts

@@ -1,0 +1,174 @@
+/*
+ * rdp.h -- C ABI of the B200-native range-Doppler + OS-CFAR path ("librdp.so").
+ *
+ * This is the drop-in boundary for the hot path of the reference FPGA design
+ * Aurellia-Beam/fpga-fmcw-radar-processor.  The reference has no software API; the
+ * boundary it defines is the `radar_core` entity (rtl/src/radar_core.vhd:11-57:
+ * generics, ADC stream in, detection stream out, control pins, status flag) and the
+ * text records its testbenches write (rtl/src/tb_radar_core.vhd:149-160).  Each entry
+ * point below cites the part of that interface it replaces.  Plain C: pointers, sizes
+ * and PODs only -- no CUDA, torch or C++ types appear in any signature.
+ *
+ * Threading: a handle is bound to one CUDA device and is not thread-safe; use one
+ * handle per GPU per host thread (the reference is a single in-order clock domain).
+ * All entry points return RDP_OK (0) or a negative RDP_E* code and never throw or
+ * exit; rdp_last_error() returns the message of the last failure.
+ * There is NO CPU fallback: rdp_create() fails with RDP_E_NO_DEVICE without a GPU.
+ */
+#ifndef RDP_H_
+#define RDP_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDP_ABI_VERSION 1
+
+enum {
+    RDP_OK = 0,
+    RDP_E_INVALID = -1,      /* bad argument / unsupported configuration          */
+    RDP_E_NO_DEVICE = -2,    /* no CUDA device, or device index out of range       */
+    RDP_E_CUDA = -3,         /* a CUDA runtime call or kernel launch failed        */
+    RDP_E_NOMEM = -4,        /* device or pinned-host allocation failed            */
+    RDP_E_CAPACITY = -5      /* n_cpi exceeds the handle's configured capacity     */
+};
+
+/* input_format */
+enum { RDP_IN_INT16_IQ = 0, RDP_IN_COMPLEX64 = 1 };
+/* mag_mode: RDP_MAG_AMB is the reference's alpha-max-beta-min (rtl/src/magnitude_calc.vhd:55-81) */
+enum { RDP_MAG_AMB = 0, RDP_MAG_ABS = 1, RDP_MAG_POW = 2, RDP_MAG_LOGPOW = 3 };
+/* cfar_axes: AS_BUILT = the RTL's *_RANGE generics act along Doppler and *_DOPPLER along
+ * range (rtl/src/os_cfar_2d.vhd:140-146,157-159); AS_NAMED = what the names say.        */
+enum { RDP_AXES_AS_BUILT = 0, RDP_AXES_AS_NAMED = 1 };
+/* cfar_edges: ZERO = window clipped to the CPI, outside cells read 0; RASTER = window on
+ * the flat range-major raster exactly as the RTL line buffer sees it (wraps into the
+ * neighbouring range line at Doppler edges; 0 before / after the CPI).                   */
+enum { RDP_EDGES_ZERO = 0, RDP_EDGES_RASTER = 1 };
+
+/* status word bits (one word per CPI) -- the sticky `status_overflow` of
+ * rtl/src/radar_core.vhd:447-456 split by cause.                                         */
+enum {
+    RDP_STATUS_DET_OVERFLOW = 1u << 0   /* more than max_dets_per_cpi detections: list truncated */
+};
+
+/*
+ * Parameters = the generics of radar_core (rtl/src/radar_core.vhd:12-20), the fixed
+ * generics it passes to os_cfar_2d (:376-382) and doppler_notch (:329-331), and its two
+ * run-time control pins mti_bypass / cfar_scale_ovr (:48-49).
+ */
+typedef struct rdp_config {
+    int32_t struct_size;       /* = sizeof(rdp_config); guards ABI drift                  */
+    int32_t n_chirps;          /* N_DOPPLER: chirps per CPI = Doppler FFT length (8..4096, power of 2) */
+    int32_t n_samples;         /* N_RANGE: samples per chirp = range FFT length (8..4096, power of 2)  */
+    int32_t n_channels;        /* receive channels per CPI (the RTL has 1)                */
+    int32_t cfar_ref_r;        /* CFAR_REF_R   (default 4)                                */
+    int32_t cfar_ref_d;        /* CFAR_REF_D   (default 4)                                */
+    int32_t cfar_guard_r;      /* CFAR_GUARD_R (default 2)                                */
+    int32_t cfar_guard_d;      /* CFAR_GUARD_D (default 1)                                */
+    int32_t rank_pct;          /* RANK_PCT     (75)                                       */
+    int32_t scale_min;         /* SCALE_MIN    (2)                                        */
+    int32_t scale_nom;         /* SCALE_NOM    (4)                                        */
+    int32_t scale_max;         /* SCALE_MAX    (6)                                        */
+    int32_t scale_override;    /* cfar_scale_ovr: 0 = adaptive, 1..7 = fixed scale        */
+    int32_t mti_mode;          /* 0 = mti_bypass, 2 = two-pulse (NOTCH_MODE), 3 = three-pulse */
+    int32_t input_format;      /* RDP_IN_*                                                */
+    int32_t mag_mode;          /* RDP_MAG_*                                               */
+    int32_t cfar_axes;         /* RDP_AXES_*                                              */
+    int32_t cfar_edges;        /* RDP_EDGES_*                                             */
+    float   window_gain;       /* 1.0; 2.0 mirrors the as-built x2 of window_multiplier.vhd:146-149 */
+    int32_t max_dets_per_cpi;  /* detection-list capacity per CPI (<= 8192)               */
+    int32_t max_cpis;          /* largest n_cpi a single rdp_process* call may pass       */
+    int32_t chunk_cpis;        /* CPIs per internal pass (0 = auto: sized so the range-major
+                                  intermediate stays L2-resident between the two FFT kernels) */
+} rdp_config;
+
+/* One detection = one `r d mag` record (rtl/src/tb_radar_core.vhd:153-159), with the CPI
+ * and channel it belongs to and TRUE cell coordinates (the RTL's 3-beat label skew,
+ * radar_core.vhd:396-411, is not reproduced).                                            */
+typedef struct rdp_det {
+    int32_t cpi;
+    int32_t channel;
+    int32_t range;
+    int32_t doppler;
+    float   mag;
+} rdp_det;
+
+typedef struct rdp_info {
+    int32_t abi_version;
+    int32_t device;
+    int32_t sm_count;
+    int32_t chunk_cpis;        /* resolved chunk size                                     */
+    int64_t scratch_bytes;     /* device memory owned by the handle                       */
+    int64_t kernel_launches;   /* kernels launched by this handle since creation          */
+    char    device_name[128];
+} rdp_info;
+
+typedef struct rdp_handle rdp_handle;
+
+/* Fills *cfg with the reference defaults (radar_core.vhd:12-20: 1024 x 128, CFAR 4/4/2/1,
+ * rank 75 %, scales 2/4/6, adaptive scale, MTI bypassed, int16 IQ input).                */
+void rdp_default_config(rdp_config* cfg);
+
+/* Replaces reset + the one-shot FFT configuration FSM (radar_core.vhd:279-301): builds
+ * window / twiddle tables, allocates scratch and the stream.                              */
+int rdp_create(const rdp_config* cfg, int32_t device, rdp_handle** out);
+int rdp_destroy(rdp_handle* h);
+const char* rdp_last_error(const rdp_handle* h);   /* h may be NULL: last create error  */
+int rdp_get_info(const rdp_handle* h, rdp_info* info);
+
+/*
+ * The whole path on DEVICE-resident buffers (the s_axis ADC stream in, the det_* stream
+ * out: radar_core.vhd:25-35).  Asynchronous on the handle's stream; rdp_sync() waits.
+ *   cube     [n_cpi][channel][chirp][sample] of {I,Q} int16 (I first) or complex64
+ *   rd_map   [n_cpi][channel][range][doppler] float32, or NULL to keep it internal
+ *   dets     [n_cpi][max_dets_per_cpi] records; the first n_dets[i] of row i are valid and
+ *            sorted by (channel, range, doppler)
+ *   n_dets   [n_cpi] detections found per CPI (may exceed max_dets_per_cpi => overflow bit)
+ *   status   [n_cpi] RDP_STATUS_* bits
+ */
+int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map,
+                       rdp_det* dets, int32_t* n_dets, uint32_t* status);
+
+/* Same with HOST buffers (pinned recommended): chunked, host->device and device->host
+ * copies overlapped with the kernels on internal streams.  Synchronous.                  */
+int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map,
+                     rdp_det* dets, int32_t* n_dets, uint32_t* status);
+
+int rdp_sync(rdp_handle* h);
+
+/* Stage taps on DEVICE buffers -- each RTL stage is separately testable (rtl/src/tb_*.vhd):
+ *   range stage   = window_multiplier + range FFT + corner_turner  (radar_core.vhd:267-327)
+ *                   cube -> x_rc [n_cpi][channel][range][chirp] complex64
+ *   doppler stage = doppler_notch + window_multiplier + Doppler FFT + magnitude_calc (:329-374)
+ *                   x_rc -> rd_map [n_cpi][channel][range][doppler] float32
+ *   cfar stage    = os_cfar_2d + non-zero filter + coordinates (:376-418)
+ *                   rd_map -> detections; cfar_out (nullable) is the RTL's dense output
+ *                   word per cell: CUT magnitude or 0.                                    */
+int rdp_range_stage(rdp_handle* h, const void* cube, int32_t n_cpi, void* x_rc);
+int rdp_doppler_stage(rdp_handle* h, const void* x_rc, int32_t n_cpi, float* rd_map);
+int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfar_out,
+                   rdp_det* dets, int32_t* n_dets, uint32_t* status);
+
+/* Device / pinned-host memory owned by the caller (so a ctypes host needs no other CUDA binding). */
+int rdp_device_alloc(rdp_handle* h, size_t bytes, void** ptr);
+int rdp_device_free(rdp_handle* h, void* ptr);
+int rdp_host_alloc(rdp_handle* h, size_t bytes, void** ptr);
+int rdp_host_free(rdp_handle* h, void* ptr);
+int rdp_copy_h2d(rdp_handle* h, void* dst_device, const void* src_host, size_t bytes);
+int rdp_copy_d2h(rdp_handle* h, void* dst_host, const void* src_device, size_t bytes);
+
+/* Measurement: CUDA-event timing on the handle's stream, per-stage accumulation, L2 flush. */
+int rdp_timer_start(rdp_handle* h);
+int rdp_timer_stop(rdp_handle* h, float* elapsed_ms);            /* synchronises            */
+int rdp_set_stage_timing(rdp_handle* h, int32_t enable);         /* events around each kernel */
+/* ms[0..3] = range, doppler, cfar, sort kernels; launches[0..3] likewise; resets the sums.  */
+int rdp_get_stage_timing(rdp_handle* h, float ms[4], int64_t launches[4]);
+int rdp_flush_l2(rdp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDP_H_ */

@@ -1,0 +1,172 @@
+"""Parity cases shared by the CPU emulation tests (tiny sizes, kernel logic) and the GPU tests
+(the parity tests proper, through the C ABI of librdp.so).  Each case takes `make_core`, a
+factory returning a RadarCore, and compares the CUDA path with the oracle on seeded inputs.
+
+Tolerances (north_star): RD map max |err| <= 1e-4 of the map peak (we assert 2e-6, float32
+FFT round-off); CFAR on an identical map: bit-exact; end-to-end detection list: identical
+except cells the oracle enumerates as within the map error of the threshold."""
+import numpy as np
+
+from oracle import float_path as fp
+from oracle import rtl_fixed as fx
+from oracle import stimulus as st
+
+MAP_TOL = 2e-6          # of map / stage peak; north_star allows 1e-4
+
+
+def rel_err(a, b):
+    return float(np.abs(np.asarray(a, np.complex128) - np.asarray(b, np.complex128)).max() / np.abs(b).max())
+
+
+def det_cells(d):
+    return {(int(x["cpi"]), int(x["channel"]), int(x["range"]), int(x["doppler"])) for x in d}
+
+
+def check_canonical(dets):
+    key = (dets["cpi"].astype(np.int64) << 48) | (dets["channel"].astype(np.int64) << 40) | \
+          (dets["range"].astype(np.int64) << 20) | dets["doppler"].astype(np.int64)
+    assert np.all(np.diff(key) > 0), "detection list not in canonical (cpi, channel, range, doppler) order"
+
+
+def case_range_stage(make_core, n_samples, n_chirps, n_ch=2, fmt="int16", seed=3):
+    cube, _ = st.synthetic_cube(2, n_ch, n_chirps, n_samples, seed=seed, dtype=fmt, n_targets=(2, 4))
+    with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, input_format=fmt, max_cpis=2) as c:
+        got = c.range_stage(cube)
+    ref = fp.range_stage(cube)
+    assert got.shape == ref.shape == (2, n_ch, n_samples, n_chirps)
+    assert rel_err(got, ref) <= MAP_TOL
+
+
+def case_corner_turn_order(make_core, n_samples=16, n_chirps=8):
+    """tb_corner_turner.vhd:146-186 analogue: an impulse of amplitude (chirp+1) at sample 0 makes the
+    range spectrum of chirp c the constant (c+1)*w[0]; out[r][d] must be in[chirp d], range slow."""
+    cube = np.zeros((n_chirps, n_samples, 2), np.int16)
+    cube[:, 0, 0] = np.arange(1, n_chirps + 1) * 100
+    with make_core(n_range=n_samples, n_doppler=n_chirps) as c:
+        got = c.range_stage(cube)[0, 0]
+    w0 = float(fp.hamming(n_samples)[0])
+    exp = np.tile((np.arange(1, n_chirps + 1) * 100 * w0)[None, :], (n_samples, 1))
+    assert np.allclose(got.real, exp, rtol=1e-6) and np.abs(got.imag).max() <= 1e-3
+
+
+def case_doppler_stage(make_core, n_samples, n_chirps, mti_mode=0, mag_mode="amb", seed=4, window_gain=1.0):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((1, 2, n_samples, n_chirps)) + 1j * rng.standard_normal((1, 2, n_samples, n_chirps)))
+    x = (x * 1000).astype(np.complex64)
+    x[0, 0, n_samples // 3] += 40000 * np.exp(2j * np.pi * 5 * np.arange(n_chirps) / n_chirps).astype(np.complex64)
+    with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=2, mti_mode=mti_mode, mag_mode=mag_mode,
+                   window_gain=window_gain) as c:
+        got = c.doppler_stage(x)
+    ref = fp.doppler_stage(x, mti_mode, mag_mode, window_gain)
+    if mag_mode == "logpow":
+        assert np.abs(got - ref).max() <= 1e-3            # dB
+    elif mag_mode == "pow":
+        assert rel_err(got, ref) <= 4 * MAP_TOL
+    else:
+        assert rel_err(got, ref) <= MAP_TOL
+
+
+def rayleigh_map(n_range, n_doppler, seed=1, n_maps=2, targets=3):
+    rng = np.random.default_rng(seed)
+    m = rng.rayleigh(100.0, size=(n_maps, n_range, n_doppler)).astype(np.float32)
+    for k in range(targets):
+        r, d = int(rng.integers(0, n_range)), int(rng.integers(0, n_doppler))
+        m[k % n_maps, r, d] = 5000.0
+        m[k % n_maps, max(r - 1, 0), d] = 1800.0
+    m[0, 0, 0] = 4000.0            # corner and edge cells exercise the edge rule
+    m[0, n_range - 1, n_doppler - 1] = 4000.0
+    m[0, n_range // 2, 0] = 3000.0
+    return m
+
+
+def case_cfar_stage(make_core, n_range, n_doppler, seed=1, **kw):
+    """CFAR stage on an identical float32 map: the dense RTL-style output and the detection list
+    must be BIT-EXACT against the oracle."""
+    m = rayleigh_map(n_range, n_doppler, seed)
+    with make_core(n_range=n_range, n_doppler=n_doppler, n_channels=2, **kw) as c:
+        dets, counts, status, dense = c.cfar_stage(m[None])
+    okw = {k: v for k, v in kw.items() if k in fp.DEFAULTS}
+    exp = np.stack([fp.cfar_stage(m[i], **okw) for i in range(2)])
+    assert np.array_equal(dense[0], exp)
+    ref = np.concatenate([fp.detections(exp[i], 0, i) for i in range(2)])
+    assert counts.tolist() == [len(ref)] and status.tolist() == [0]
+    assert len(ref) > 0
+    for f in ("cpi", "channel", "range", "doppler", "mag"):
+        assert np.array_equal(dets[f], ref[f]), f
+    check_canonical(dets)
+
+
+def case_cfar_tb_map(make_core):
+    """rtl/src/tb_os_cfar_2d.vhd:42-75 map, (3,2,1,1): the float CUDA CFAR with a fixed scale equals
+    the bit-exact integer restatement of os_cfar_2d.vhd on this integer-valued map."""
+    m = st.cfar_tb_map()
+    for edges in ("zero", "raster"):
+        for ovr in (2, 4):
+            with make_core(n_range=64, n_doppler=32, cfar_ref_r=3, cfar_ref_d=2, cfar_guard_r=1, cfar_guard_d=1,
+                           scale_override=ovr, cfar_edges=edges) as c:
+                dets, counts, status, dense = c.cfar_stage(m.astype(np.float32)[None, None])
+            exp = fx.os_cfar_2d(m, 3, 2, 1, 1, scale_override=ovr, edges=edges)
+            assert np.array_equal(dense[0, 0].astype(np.uint32), exp)
+            cells = {(int(r), int(d)) for r, d in zip(dets["range"], dets["doppler"])}
+            assert (30, 16) in cells and (50, 8) in cells           # T1: both targets found (:123-134)
+
+
+def case_end_to_end(make_core, n_cpi, n_ch, n_chirps, n_samples, seed=11, fmt="int16", **kw):
+    cube, _ = st.synthetic_cube(n_cpi, n_ch, n_chirps, n_samples, seed=seed, dtype=fmt)
+    with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, input_format=fmt, max_cpis=n_cpi, **kw) as c:
+        rd_map, dets, n_dets, status = c.process(cube)
+        launches = c.info()["kernel_launches"]
+    okw = {k: v for k, v in kw.items() if k in fp.DEFAULTS}
+    ref_map, ref_dets, ref_counts = fp.process_batch(cube, **okw)
+    err = float(np.abs(rd_map - ref_map).max())
+    assert err <= MAP_TOL * float(ref_map.max())
+    assert status.tolist() == [0] * n_cpi and launches > 0
+    check_canonical(dets)
+    assert int(n_dets.sum()) == len(dets)
+    eps = max(4.0 * err, 1e-7 * float(ref_map.max()))
+    diff = det_cells(dets) ^ det_cells(ref_dets)
+    amb_maps = {}
+    for (i, ch, r, d) in diff:
+        if (i, ch) not in amb_maps:
+            amb_maps[(i, ch)] = fp.ambiguous_cells(ref_map[i, ch], eps, **okw)
+        assert amb_maps[(i, ch)][r, d], f"detection mismatch at {(i, ch, r, d)} is not near-threshold"
+    assert len(diff) <= max(2, len(ref_dets) // 50)
+    assert len(ref_dets) > 0
+    return len(dets), len(diff)
+
+
+def case_overflow_flag(make_core):
+    m = rayleigh_map(64, 64, seed=5, n_maps=1)
+    m[0, 10:30, 10:30:3] = 9000.0                          # many isolated strong cells
+    with make_core(n_range=64, n_doppler=64, max_dets_per_cpi=8, scale_override=1) as c:
+        dets, counts, status, _ = c.cfar_stage(m[None], want_dense=False)
+    assert counts[0] > 8 and status[0] & 1 and len(dets) == 8
+    check_canonical(dets)
+
+
+def case_chunking_invariance(make_core, n_samples=64, n_chirps=32):
+    cube, _ = st.synthetic_cube(3, 2, n_chirps, n_samples, seed=21, sigma=25.0, n_targets=(1, 3))
+    out = []
+    for chunk in (1, 2, 3):
+        with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=2, max_cpis=3, chunk_cpis=chunk) as c:
+            assert c.info()["chunk_cpis"] == chunk
+            out.append(c.process(cube))
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0])
+        assert np.array_equal(o[1], out[0][1]) and np.array_equal(o[2], out[0][2])
+
+
+def case_golden_chirp(make_core, golden_chirp_1024, n_chirps=16):
+    """data/golden_input_chirp.txt[0:1024] replicated over the chirps with a Doppler ramp of bin 3:
+    the RD map must peak at range bin 290 (0.283333 * 1024), Doppler bin 3."""
+    base = golden_chirp_1024[:, 0].astype(np.float64) + 1j * golden_chirp_1024[:, 1]
+    ramp = np.exp(2j * np.pi * 3 * np.arange(n_chirps) / n_chirps)[:, None]
+    z = 0.5 * base[None, :] * ramp
+    cube = np.stack([np.round(z.real), np.round(z.imag)], axis=-1).astype(np.int16)
+    with make_core(n_range=1024, n_doppler=n_chirps) as c:
+        rd_map, dets, n_dets, status = c.process(cube)
+    ref_map, ref_dets = fp.process_cpi(cube)
+    r, d = np.unravel_index(np.argmax(rd_map[0, 0]), rd_map[0, 0].shape)
+    assert (int(r), int(d)) == (290, 3)
+    assert float(np.abs(rd_map[0] - ref_map).max()) <= MAP_TOL * float(ref_map.max())
+    assert (0, 0, 290, 3) in det_cells(dets)

@@ -1,0 +1,73 @@
+"""Kernel LOGIC under host emulation (CPU, no GPU): the same kernel sources as librdp.so,
+compiled with g++ against csrc/emu/cuda_emu.h (one OS thread per CUDA thread), driven through
+the same C ABI and compared with the oracle at tiny sizes.  This is a development aid that
+catches indexing / counting mistakes before GPU time is spent; it is not a product path
+(the product loader refuses this library) and proves nothing about the real device -- the GPU
+parity tests in test_gpu_parity.py do that."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fpga_fmcw_radar_processor_b200 as rdp
+import parity_cases as pc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu", "librdp_emu.so")
+
+
+@pytest.fixture(scope="module")
+def make_core():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "fpga-fmcw-radar-processor_b200"), "emu"])
+
+    def factory(**kw):
+        return rdp.RadarCore(library=EMU, _test_allow_emulator=True, **kw)
+    return factory
+
+
+@pytest.mark.parametrize("ns,nc,fmt", [(64, 32, "int16"), (128, 16, "complex64"), (16, 8, "int16"), (512, 16, "int16")])
+def test_range_stage(make_core, ns, nc, fmt):
+    pc.case_range_stage(make_core, ns, nc, fmt=fmt)
+
+
+def test_corner_turn_order(make_core):
+    pc.case_corner_turn_order(make_core)
+
+
+@pytest.mark.parametrize("mti,mag", [(0, "amb"), (2, "abs"), (3, "pow"), (0, "logpow")])
+def test_doppler_stage(make_core, mti, mag):
+    pc.case_doppler_stage(make_core, 16, 64, mti, mag)
+
+
+def test_doppler_stage_256(make_core):
+    pc.case_doppler_stage(make_core, 8, 256, 2, "amb", window_gain=2.0)
+
+
+@pytest.mark.parametrize("nr,nd,kw", [
+    (64, 128, dict()),                                          # radar_core defaults, 2 x 2 tiles
+    (16, 32, dict(cfar_edges="raster")),                        # partial tile
+    (64, 32, dict(cfar_axes="as_named", scale_override=3)),
+    (32, 64, dict(cfar_ref_r=3, cfar_ref_d=2, cfar_guard_r=1, cfar_guard_d=1)),
+    (32, 32, dict(cfar_ref_r=1, cfar_ref_d=2, cfar_guard_r=0, cfar_guard_d=1, cfar_edges="raster")),   # generic kernel
+    (32, 64, dict(rank_pct=50, scale_min=3, scale_nom=5, scale_max=7)),
+    (32, 64, dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2)),   # BASELINE config 4 "wide"
+])
+def test_cfar_stage_bit_exact(make_core, nr, nd, kw):
+    pc.case_cfar_stage(make_core, nr, nd, **kw)
+
+
+def test_cfar_tb_map(make_core):
+    pc.case_cfar_tb_map(make_core)
+
+
+def test_end_to_end(make_core):
+    pc.case_end_to_end(make_core, 2, 2, 32, 64)
+
+
+def test_overflow_flag(make_core):
+    pc.case_overflow_flag(make_core)
+
+
+def test_chunking_invariance(make_core):
+    pc.case_chunking_invariance(make_core)

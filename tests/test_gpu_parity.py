@@ -1,0 +1,184 @@
+"""GPU parity tests proper: the CUDA path, through the C ABI of librdp.so, against the oracle.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+Nothing here reads /root/reference; reference-derived inputs come from tests/golden/."""
+import os
+
+import numpy as np
+import pytest
+
+import fpga_fmcw_radar_processor_b200 as rdp
+import parity_cases as pc
+from oracle import float_path as fp
+from oracle import stimulus as st
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def make_core():
+    lib = rdp.load_library()                       # raises if librdp.so is missing: no fallback
+    assert not hasattr(lib, "rdp_emu_marker")
+
+    def factory(**kw):
+        return rdp.RadarCore(**kw)
+    with factory(n_range=64, n_doppler=32) as c:
+        assert "emulator" not in c.info()["device_name"]
+    return factory
+
+
+# ---- stage taps -------------------------------------------------------------------------------
+@pytest.mark.parametrize("ns,nc,fmt", [(512, 256, "int16"), (512, 256, "complex64"), (1024, 128, "int16"),
+                                        (64, 32, "int16"), (128, 64, "complex64"), (256, 16, "int16"),
+                                        (16, 8, "int16"), (8, 16, "int16"), (32, 512, "int16"),
+                                        (2048, 32, "int16"), (4096, 16, "complex64")])
+def test_range_stage(make_core, ns, nc, fmt):
+    pc.case_range_stage(make_core, ns, nc, fmt=fmt)
+
+
+def test_corner_turn_order(make_core):
+    pc.case_corner_turn_order(make_core)
+    pc.case_corner_turn_order(make_core, 512, 256)
+
+
+@pytest.mark.parametrize("ns,nc,mti,mag", [(64, 256, 0, "amb"), (64, 256, 2, "abs"), (64, 128, 3, "pow"),
+                                            (32, 512, 0, "logpow"), (16, 1024, 2, "amb"), (16, 2048, 0, "amb"),
+                                            (8, 4096, 3, "amb"), (64, 64, 2, "amb"), (64, 32, 0, "amb"),
+                                            (64, 16, 0, "amb"), (64, 8, 2, "amb")])
+def test_doppler_stage(make_core, ns, nc, mti, mag):
+    pc.case_doppler_stage(make_core, ns, nc, mti, mag)
+
+
+def test_doppler_stage_window_gain(make_core):
+    pc.case_doppler_stage(make_core, 32, 256, 2, "amb", window_gain=2.0)
+
+
+@pytest.mark.parametrize("nr,nd,kw", [
+    (512, 256, dict()),
+    (1024, 128, dict(cfar_edges="raster")),
+    (128, 64, dict(cfar_axes="as_named")),
+    (64, 32, dict(cfar_ref_r=3, cfar_ref_d=2, cfar_guard_r=1, cfar_guard_d=1)),
+    (64, 32, dict(cfar_ref_r=3, cfar_ref_d=2, cfar_guard_r=1, cfar_guard_d=1, cfar_axes="as_named", cfar_edges="raster")),
+    (128, 128, dict(cfar_ref_r=2, cfar_ref_d=2, cfar_guard_r=1, cfar_guard_d=1)),
+    (64, 64, dict(cfar_ref_r=1, cfar_ref_d=2, cfar_guard_r=0, cfar_guard_d=1, cfar_edges="raster")),   # generic kernel
+    (256, 128, dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2)),                      # wide
+    (256, 128, dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2, cfar_axes="as_named", cfar_edges="raster")),
+    (128, 64, dict(scale_override=1)), (128, 64, dict(scale_override=4)), (128, 64, dict(scale_override=7)),
+    (128, 64, dict(rank_pct=50, scale_min=3, scale_nom=5, scale_max=7)),
+    (128, 64, dict(rank_pct=100)), (128, 64, dict(rank_pct=0)),
+    (8, 8, dict()), (16, 256, dict(cfar_edges="raster")),
+])
+def test_cfar_stage_bit_exact(make_core, nr, nd, kw):
+    pc.case_cfar_stage(make_core, nr, nd, **kw)
+
+
+@pytest.mark.parametrize("seed", [2, 3, 4])
+def test_cfar_stage_bit_exact_seeds(make_core, seed):
+    pc.case_cfar_stage(make_core, 512, 256, seed=seed)
+
+
+def test_cfar_tb_map(make_core):
+    pc.case_cfar_tb_map(make_core)
+
+
+def test_cfar_empty_and_flat_maps(make_core):
+    """All-zero map: no detections (a CUT of 0 can never be one, radar_core.vhd:415); constant map:
+    none either (cut > s*x_k fails for s >= 1)."""
+    with make_core(n_range=64, n_doppler=64) as c:
+        for m in (np.zeros((1, 1, 64, 64), np.float32), np.full((1, 1, 64, 64), 7.0, np.float32)):
+            dets, counts, status, dense = c.cfar_stage(m)
+            ref = fp.cfar_stage(m[0, 0])
+            assert np.array_equal(dense[0, 0], ref)
+            assert counts.tolist() == [int(np.count_nonzero(ref))]
+
+
+# ---- whole path ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_cpi,n_ch,nc,ns,fmt,kw", [
+    (2, 3, 256, 512, "int16", dict()),                                   # BASELINE config 3 shape
+    (2, 2, 256, 512, "complex64", dict(mti_mode=2)),
+    (3, 1, 128, 1024, "int16", dict()),                                  # config 2 (RTL-native) shape
+    (1, 1, 128, 1024, "int16", dict(cfar_edges="raster", mag_mode="abs", window_gain=2.0)),
+    (2, 2, 64, 128, "int16", dict(mti_mode=3, cfar_axes="as_named")),
+    (1, 1, 1024, 4096, "complex64", dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2)),   # config 4 shape
+])
+def test_end_to_end(make_core, n_cpi, n_ch, nc, ns, fmt, kw):
+    pc.case_end_to_end(make_core, n_cpi, n_ch, nc, ns, fmt=fmt, **kw)
+
+
+def test_config2_three_targets(make_core):
+    """BASELINE config 2: RTL-native shape, targets (100,+5), (500,-10 = 118), (750,40)."""
+    tg = [(100, 5, 8000.0), (500, 118, 5000.0), (750, 40, 3000.0)]
+    cube, _ = st.synthetic_cube(1, 1, 128, 1024, seed=1234, sigma=12.0, fixed_targets=tg)
+    with make_core(n_range=1024, n_doppler=128) as c:
+        rd_map, dets, n_dets, status = c.process(cube)
+    cells = pc.det_cells(dets)
+    for (r, d, _) in tg:
+        assert (0, 0, r, d) in cells
+    # detections cluster on the targets only: each lies on a target's range row or Doppler column
+    for (_, _, r, d) in cells:
+        assert any(abs(r - tr) <= 3 or d == td for (tr, td, _) in tg)
+
+
+def test_old_tb_stimulus_structure(make_core, golden_dir):
+    """rtl/old/tb_radar_core.vhd two-target stimulus through the CUDA path reproduces the structure
+    of data/radar_output.txt (energy in rows {99,100,101},{499,500,501})."""
+    ro = np.load(os.path.join(golden_dir, "radar_output_summary.npz"))
+    cube = st.old_tb_radar_core_cube(rng=np.random.default_rng(1))
+    with make_core(n_range=1024, n_doppler=128) as c:
+        rd_map, dets, _, _ = c.process(cube)
+    m = rd_map[0, 0]
+    assert set(np.argsort(m.max(axis=1))[::-1][:6].tolist()) == set(np.argsort(ro["row_max"])[::-1][:6].tolist())
+    assert int(np.argmax(m[100])) == 5 and int(np.argmax(m[500])) == 118
+
+
+def test_golden_chirp_peak_bin_290(make_core, golden_dir):
+    pc.case_golden_chirp(make_core, np.load(os.path.join(golden_dir, "golden_input_chirp_1024.npy")))
+
+
+def test_overflow_flag(make_core):
+    pc.case_overflow_flag(make_core)
+
+
+def test_chunking_invariance(make_core):
+    pc.case_chunking_invariance(make_core)
+    pc.case_chunking_invariance(make_core, 512, 256)
+
+
+def test_device_resident_api_matches_host_api(make_core):
+    cube, _ = st.synthetic_cube(4, 2, 64, 128, seed=31)
+    with make_core(n_range=128, n_doppler=64, n_channels=2, max_cpis=4, chunk_cpis=3) as c:
+        m_h, d_h, n_h, s_h = c.process(cube)
+        d_cube = c.device_buffer(cube.nbytes).upload(cube)
+        d_map = c.device_buffer(m_h.nbytes)
+        d_dets = c.device_buffer(4 * c.max_dets_per_cpi * rdp.DET_DTYPE.itemsize)
+        d_cnt, d_st = c.device_buffer(16), c.device_buffer(16)
+        c.process_device(d_cube, 4, d_map, d_dets, d_cnt, d_st)
+        c.sync()
+        dets, counts = c.unpack_device_dets(d_dets, d_cnt, 4)
+        assert np.array_equal(d_map.download(m_h.shape, np.float32), m_h)
+        assert np.array_equal(dets, d_h) and np.array_equal(counts, n_h)
+
+
+# ---- full-size, size-independent properties ---------------------------------------------------------
+def test_full_size_properties(make_core):
+    """BASELINE config-3 shape (256 x 512 x 12 channels), 4 CPIs: determinism, exact x2 scaling
+    (a power-of-two gain changes no float32 rounding, so the map doubles exactly and the CFAR
+    decisions are identical), Parseval on the range stage, oracle parity on a sampled map."""
+    n_cpi, n_ch, nc, ns = 4, 12, 256, 512
+    cube, _ = st.synthetic_cube(n_cpi, n_ch, nc, ns, seed=100, amp=(500.0, 6000.0))
+    with make_core(n_range=ns, n_doppler=nc, n_channels=n_ch, max_cpis=n_cpi) as c:
+        m1, d1, n1, s1 = c.process(cube)
+        m2, d2, n2, s2 = c.process(cube)
+        assert np.array_equal(m1, m2) and np.array_equal(d1, d2)                     # deterministic
+        m3, d3, n3, s3 = c.process((cube * 2).astype(np.int16))
+        assert np.array_equal(m3, 2.0 * m1)                                          # linear, exactly
+        for f in ("cpi", "channel", "range", "doppler"):
+            assert np.array_equal(d3[f], d1[f])                                      # scale-invariant CFAR
+        x = c.range_stage(cube[:1])
+        z = fp.to_complex(cube[:1]) * fp.hamming(ns)
+        lhs = float((np.abs(x.astype(np.complex128)) ** 2).sum())
+        rhs = float(ns * (np.abs(z) ** 2).sum())
+        assert abs(lhs - rhs) <= 1e-5 * rhs                                          # Parseval
+    ref = fp.rd_map(cube[2, 7]).astype(np.float32)
+    assert float(np.abs(m1[2, 7] - ref).max()) <= pc.MAP_TOL * float(ref.max())
+    pc.check_canonical(d1)
+    assert s1.tolist() == [0] * n_cpi and len(d1) > 12 * n_cpi
