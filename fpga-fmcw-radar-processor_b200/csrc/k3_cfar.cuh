@@ -1,17 +1,27 @@
-// k3_cfar.cuh -- K3: 2D ordered-statistic CFAR + non-zero filter + detection records.
+// k3_cfar.cuh -- K3: 2D ordered-statistic CFAR, and K4: ordered compaction to detection records.
 //
-// Replaces os_cfar_2d (rtl/src/os_cfar_2d.vhd:140-217) and the detection filter / coordinate
+// Replaces os_cfar_2d (rtl/src/os_cfar_2d.vhd:140-217) and the non-zero filter / coordinate
 // counters of rtl/src/radar_core.vhd:396-418.  The RTL bubble-sorts the N_REF reference cells
 // of every cell under test (:172-178).  Here nothing is sorted: with k = rank_idx,
 //     cut > s * x_(k)   <=>   #{ref : fl(ref * s) < cut} >= k + 1
 //     x_(k) > a         <=>   #{ref <= a} <= k
 //     x_(k) < a         <=>   #{ref <  a} >= k + 1
-// (identities checked in tests/test_oracle_fixed.py).  Phase 1 tests every
-// cell against the most permissive scale s1 (scale_override, or the smallest of
-// SCALE_MIN/NOM/MAX) from a shared-memory tile of pre-scaled magnitudes; each thread owns a
-// strip of S cells along range so a loaded reference value feeds up to S counters.  The few
-// survivors (~0.4 % of noise cells) go to phase 2: a warp per survivor evaluates the sum
-// (float64), the adaptive scale (:189-199) and the final test exactly.
+// (identities checked in tests/test_oracle_fixed.py).
+//
+// Phase 1 (every cell, the ALU-bound bulk): a CONSERVATIVE pre-filter against the most
+// permissive scale s1 (scale_override, or the smallest of SCALE_MIN/NOM/MAX).  The tile is
+// staged in shared memory twice: raw float32, and fl(v*s1) truncated to bfloat16 and duplicated
+// into both halves of a word.  Each thread owns S cells along range (one Doppler column), holds
+// their cut values rounded UP to bfloat16 packed two per register, and counts with one packed
+// compare per two (cell, reference) pairs (HSET2.BF16_V2 -> 0xFFFF masks, summed two at a time by
+// IADD3): measured 3.5x the rate of FSETP + predicated add on B200
+// (profiles/r1_mb_cmpacc_b200.txt).  ref_lo <= fl(v*s1) < cut <= cut_hi, so the packed count never
+// undercounts: no true detection is rejected.
+// Phase 2 (survivors only, ~0.5 % of noise cells + target cells): one warp per survivor decides
+// EXACTLY in float32 from the raw tile -- the s1 test, then (adaptive mode) float64 sum -> mean
+// -> scale 2/4/6 (:189-199) -> final test.  Decisions set bits in a per-tile bitmask.
+// K4 walks the bitmask of each CPI in (channel, range, doppler) order and writes the records, so
+// the list is canonical without a sort and truncation on overflow is deterministic.
 //   algorithmic HBM bytes / cell: 4 read (+4 if the dense RTL-style output is requested).
 #pragma once
 #include "rdp_common.cuh"
@@ -27,6 +37,7 @@ struct CfarArgs {
     int adaptive;                           // 1: scale chosen per cell, 0: s1 is the fixed scale
     int raster;                             // cfar_edges
     int max_dets;
+    int words_per_row;                      // bitmask words per range line = ceil(n_doppler / 32)
 };
 
 // magnitude of flat cell (line, col) of one map under the edge rule
@@ -40,18 +51,27 @@ __device__ __forceinline__ float cfar_fetch(const float* __restrict__ m, int lin
                ? __ldg(m + (long long)line * n_doppler + col) : 0.0f;
 }
 
-__device__ __forceinline__ void cfar_emit(const CfarArgs& a, long long map, int line, int col, float mag,
-                                          rdp_det* __restrict__ dets, int* __restrict__ counts) {
-    const int cpi = (int)(map / a.n_channels), ch = (int)(map % a.n_channels);
-    const int slot = atomicAdd(counts + cpi, 1);
-    if (slot < a.max_dets) {
-        rdp_det d;
-        d.cpi = cpi; d.channel = ch; d.range = line; d.doppler = col; d.mag = mag;
-        dets[(long long)cpi * a.max_dets + slot] = d;
+// 0xFFFF in each half where a.half < b.half (bfloat16 compare)
+__device__ __forceinline__ uint32_t bf16x2_lt_mask(uint32_t a, uint32_t b) {
+#ifdef RDP_EMU
+    uint32_t r = 0;
+    for (int h = 0; h < 2; ++h) {
+        float fa = __int_as_float((int)(((a >> (16 * h)) & 0xffffu) << 16));
+        float fb = __int_as_float((int)(((b >> (16 * h)) & 0xffffu) << 16));
+        if (fa < fb) r |= 0xffffu << (16 * h);
     }
+    return r;
+#else
+    uint32_t r;
+    asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#endif
 }
+// float (>= 0) -> bfloat16 bits rounded toward zero / toward +inf
+__device__ __forceinline__ uint32_t bf16_down(float v) { return (uint32_t)__float_as_int(v) >> 16; }
+__device__ __forceinline__ uint32_t bf16_up(float v) { return ((uint32_t)__float_as_int(v) + 0xffffu) >> 16; }
 
-// Exact decision for one cell by one warp (all 32 lanes call this with the same cell).
+// Exact decision for one cell by one warp from GLOBAL memory (generic kernel).
 template <int MAXQ>
 __device__ __forceinline__ bool cfar_exact_warp(const CfarArgs& a, const float* __restrict__ m,
                                                 int line, int col, float cut, int lane) {
@@ -104,18 +124,54 @@ struct K3Shape {
     static constexpr int SROWS = TROWS + 2 * HL, SCOLS = TCOLS + 2 * HC;
     static constexpr int WIN = (2 * HL + 1) * (2 * HC + 1);
     static constexpr int MAXQ = (WIN + 31) / 32;
-    static constexpr size_t smem_bytes() { return sizeof(float) * SROWS * SCOLS + sizeof(int) * (TROWS * TCOLS + 4); }
+    static constexpr int TWORDS = (TCOLS + 31) / 32;              // bitmask words per tile row
+    static constexpr size_t smem_bytes() {
+        return sizeof(float) * 2 * SROWS * SCOLS + sizeof(int) * (TROWS * TCOLS + TROWS * TWORDS + 4);
+    }
+};
+
+// one packed compare for cells (2p, 2p+1) of the strip against tile row lr, if either is a reference
+template <int HL, int GL, bool GUARD_COL, int P, int LR>
+__device__ __forceinline__ void k3_pair(uint32_t v, const uint32_t (&cb)[4], const uint32_t (&cl)[4],
+                                        const uint32_t (&ch)[4], uint32_t (&acc)[4]) {
+    constexpr int dl0 = LR - 2 * P - HL, dl1 = dl0 - 1;            // line offset of row LR from cell 2p, 2p+1
+    constexpr bool in0 = dl0 >= -HL && dl0 <= HL && !(GUARD_COL && dl0 >= -GL && dl0 <= GL);
+    constexpr bool in1 = dl1 >= -HL && dl1 <= HL && !(GUARD_COL && dl1 >= -GL && dl1 <= GL);
+    if (in0 && in1) acc[P] -= bf16x2_lt_mask(v, cb[P]);
+    else if (in0) acc[P] -= bf16x2_lt_mask(v, cl[P]);
+    else if (in1) acc[P] -= bf16x2_lt_mask(v, ch[P]);
+}
+
+template <int HL, int GL, bool GUARD_COL, int LR, int NROWS>
+struct K3Rows {
+    static __device__ __forceinline__ void run(const uint32_t* __restrict__ tp, int pitch, const uint32_t (&cb)[4],
+                                               const uint32_t (&cl)[4], const uint32_t (&ch)[4], uint32_t (&acc)[4]) {
+        const uint32_t v = tp[LR * pitch];
+        k3_pair<HL, GL, GUARD_COL, 0, LR>(v, cb, cl, ch, acc);
+        k3_pair<HL, GL, GUARD_COL, 1, LR>(v, cb, cl, ch, acc);
+        k3_pair<HL, GL, GUARD_COL, 2, LR>(v, cb, cl, ch, acc);
+        k3_pair<HL, GL, GUARD_COL, 3, LR>(v, cb, cl, ch, acc);
+        K3Rows<HL, GL, GUARD_COL, LR + 1, NROWS>::run(tp, pitch, cb, cl, ch, acc);
+    }
+};
+template <int HL, int GL, bool GUARD_COL, int NROWS>
+struct K3Rows<HL, GL, GUARD_COL, NROWS, NROWS> {
+    static __device__ __forceinline__ void run(const uint32_t* __restrict__, int, const uint32_t (&)[4],
+                                               const uint32_t (&)[4], const uint32_t (&)[4], uint32_t (&)[4]) {}
 };
 
 template <int HL, int HC, int GL, int GC, int S, int TCOLS>
 __global__ void __launch_bounds__(256)
-k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, rdp_det* __restrict__ dets,
-               int* __restrict__ counts, CfarArgs a, int tiles_r, int tiles_c) {
+k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, uint32_t* __restrict__ det_bits,
+               CfarArgs a, int tiles_r, int tiles_c) {
+    static_assert(S == 8, "the strip is four packed pairs");
     using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
     RDP_DYN_SMEM(smem_raw);
-    float* tile = reinterpret_cast<float*>(smem_raw);
-    int* surv = reinterpret_cast<int*>(tile + Sh::SROWS * Sh::SCOLS);
-    int* n_surv = surv + Sh::TROWS * TCOLS;
+    float* tf = reinterpret_cast<float*>(smem_raw);                           // raw magnitudes
+    uint32_t* th = reinterpret_cast<uint32_t*>(tf + Sh::SROWS * Sh::SCOLS);   // bf16x2 (lo, lo) of fl(v*s1)
+    int* surv = reinterpret_cast<int*>(th + Sh::SROWS * Sh::SCOLS);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(surv + Sh::TROWS * TCOLS);
+    int* n_surv = reinterpret_cast<int*>(bits + Sh::TROWS * Sh::TWORDS);
 
     const long long tile_id = blockIdx.x;
     const long long map = tile_id / (tiles_r * tiles_c);
@@ -124,158 +180,253 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, r
     const float* m = rd_map + map * (long long)a.n_range * a.n_doppler;
 
     if (threadIdx.x == 0) *n_surv = 0;
-    for (int i = threadIdx.x; i < Sh::SROWS * Sh::SCOLS; i += 256) {
-        const int lr = i / Sh::SCOLS, lc = i % Sh::SCOLS;
-        const float v = cfar_fetch(m, r0 - HL + lr, c0 - HC + lc, a.n_range, a.n_doppler, a.raster);
-        tile[i] = __fmul_rn(v, a.s1);
-    }
-    __syncthreads();
-
-    const int tx = threadIdx.x % TCOLS, ty = threadIdx.x / TCOLS;
-    const int col = c0 + tx;
-    float cut[S];
-    int cnt[S];
-    RDP_UNROLL
-    for (int j = 0; j < S; ++j) {
-        const int line = r0 + ty * S + j;
-        cut[j] = (line < a.n_range && col < a.n_doppler) ? __ldg(m + (long long)line * a.n_doppler + col) : 0.0f;
-        cnt[j] = 0;
-    }
-    const float* tp = tile + (ty * S) * Sh::SCOLS + tx + HC;
-    for (int dc = -HC; dc <= HC; ++dc) {
-        if (dc >= -GC && dc <= GC) {                      // columns crossing the guard box
+    for (int i = threadIdx.x; i < Sh::TROWS * Sh::TWORDS; i += 256) bits[i] = 0u;
+    {   // tile + halo, one warp per tile row (coalesced, no per-element index arithmetic)
+        const int lw = threadIdx.x / 32, ll = threadIdx.x % 32;
+        for (int lr = lw; lr < Sh::SROWS; lr += 8) {
+            const int line = r0 - HL + lr;
+            const bool row_ok = a.raster || (line >= 0 && line < a.n_range);
+            const long long row_base = (long long)line * a.n_doppler;
             RDP_UNROLL
-            for (int lr = 0; lr < S + 2 * HL; ++lr) {
-                const float v = tp[lr * Sh::SCOLS + dc];
-                RDP_UNROLL
-                for (int j = 0; j < S; ++j) {
-                    const int dl = lr - j - HL;
-                    if (dl >= -HL && dl <= HL && !(dl >= -GL && dl <= GL)) cnt[j] += (v < cut[j]) ? 1 : 0;
-                }
-            }
-        } else {
-            RDP_UNROLL
-            for (int lr = 0; lr < S + 2 * HL; ++lr) {
-                const float v = tp[lr * Sh::SCOLS + dc];
-                RDP_UNROLL
-                for (int j = 0; j < S; ++j) {
-                    const int dl = lr - j - HL;
-                    if (dl >= -HL && dl <= HL) cnt[j] += (v < cut[j]) ? 1 : 0;
+            for (int k = 0; k < (Sh::SCOLS + 31) / 32; ++k) {
+                const int lc = ll + 32 * k;
+                if (lc < Sh::SCOLS) {
+                    const int c = c0 - HC + lc;
+                    float v = 0.0f;
+                    if (a.raster) {
+                        const long long flat = row_base + c;
+                        if (flat >= 0 && flat < (long long)a.n_range * a.n_doppler) v = __ldg(m + flat);
+                    } else if (row_ok && c >= 0 && c < a.n_doppler) {
+                        v = __ldg(m + row_base + c);
+                    }
+                    tf[lr * Sh::SCOLS + lc] = v;
+                    const uint32_t lo = bf16_down(__fmul_rn(v, a.s1));
+                    th[lr * Sh::SCOLS + lc] = lo | (lo << 16);
                 }
             }
         }
+    }
+    __syncthreads();
+
+    // ---- phase 1: conservative packed pre-filter ---------------------------------------------------
+    const int tx = threadIdx.x % TCOLS, ty = threadIdx.x / TCOLS;
+    const int col = c0 + tx;
+    uint32_t cb[4], cl[4], ch[4], acc[4];
+    bool force[S];
+    RDP_UNROLL
+    for (int p = 0; p < 4; ++p) {
+        const float c_lo = tf[(ty * S + 2 * p + HL) * Sh::SCOLS + tx + HC];
+        const float c_hi = tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + HC];
+        const uint32_t h0 = bf16_up(c_lo), h1 = bf16_up(c_hi);
+        cb[p] = h0 | (h1 << 16);
+        cl[p] = h0;
+        ch[p] = h1 << 16;
+        acc[p] = 0u;
+        // bfloat16 subnormal range: leave the decision to the exact phase
+        force[2 * p] = c_lo > 0.0f && c_lo < 1e-36f;
+        force[2 * p + 1] = c_hi > 0.0f && c_hi < 1e-36f;
+    }
+    const uint32_t* tp = th + (ty * S) * Sh::SCOLS + tx + HC;
+    for (int dc = -HC; dc <= HC; ++dc) {
+        if (dc >= -GC && dc <= GC) K3Rows<HL, GL, true, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
+        else K3Rows<HL, GL, false, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
     }
     RDP_UNROLL
     for (int j = 0; j < S; ++j) {
         const int line = r0 + ty * S + j;
         if (line < a.n_range && col < a.n_doppler) {
-            const bool pass = cnt[j] >= a.rank_idx + 1;
-            if (cfar_out) cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)line * a.n_doppler + col] =
-                (pass && !a.adaptive) ? cut[j] : 0.0f;
-            if (pass) {
-                if (a.adaptive) surv[atomicAdd(n_surv, 1)] = ((ty * S + j) << 16) | tx;
-                else cfar_emit(a, map, line, col, cut[j], dets, counts);
-            }
+            const uint32_t lo16 = acc[j >> 1] & 0xffffu;
+            const uint32_t cnt = (j & 1) ? (((acc[j >> 1] >> 16) + lo16) & 0xffffu) : lo16;
+            if (cfar_out) cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)line * a.n_doppler + col] = 0.0f;
+            if ((int)cnt >= a.rank_idx + 1 || force[j]) surv[atomicAdd(n_surv, 1)] = ((ty * S + j) << 16) | tx;
         }
     }
-    if (!a.adaptive) return;
     __syncthreads();
+
+    // ---- phase 2: exact decision, one warp per survivor, from the raw tile ----------------------------
+    // Window slots are dealt to lanes (slot = lane + 32 q); guard / padding slots read as 0 and their known
+    // contribution to each count is subtracted.  Counting uses the sign bit of an exact float subtraction.
     const int ns = *n_surv;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    constexpr int NZ = 32 * Sh::MAXQ - (Sh::WIN - (2 * GL + 1) * (2 * GC + 1));     // non-reference slots per warp
+    int off[Sh::MAXQ];
+    bool isref[Sh::MAXQ];
+    RDP_UNROLL
+    for (int q = 0; q < Sh::MAXQ; ++q) {
+        const int idx = lane + 32 * q;
+        const int dl = idx / (2 * HC + 1) - HL, dc = idx % (2 * HC + 1) - HC;
+        isref[q] = idx < Sh::WIN && !(dl >= -GL && dl <= GL && dc >= -GC && dc <= GC);
+        off[q] = isref[q] ? dl * Sh::SCOLS + dc : 0;
+    }
+    const bool n_ref_pow2 = (a.n_ref & (a.n_ref - 1)) == 0;
+    const double inv_n = 1.0 / (double)a.n_ref;
     for (int i = warp; i < ns; i += 8) {
         const int code = surv[i];
-        const int line = r0 + (code >> 16), c = c0 + (code & 0xffff);
-        const float cv = __ldg(m + (long long)line * a.n_doppler + c);
-        const bool det = cfar_exact_warp<Sh::MAXQ>(a, m, line, c, cv, lane);
-        if (det && lane == 0) {
-            if (cfar_out) cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)line * a.n_doppler + c] = cv;
-            cfar_emit(a, map, line, c, cv, dets, counts);
+        const int tl = code >> 16, tcx = code & 0xffff;
+        const float* ctr = tf + (tl + HL) * Sh::SCOLS + tcx + HC;
+        const float cut = *ctr;
+        float v[Sh::MAXQ];
+        RDP_UNROLL
+        for (int q = 0; q < Sh::MAXQ; ++q) {
+            const float t = ctr[off[q]];
+            v[q] = isref[q] ? t : 0.0f;
         }
+        float scale = a.s1;
+        if (a.adaptive) {
+            double s = 0.0;
+            RDP_UNROLL
+            for (int q = 0; q < Sh::MAXQ; ++q) s += (double)v[q];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            // mean = float32(S / N_REF)  (os_cfar_2d.vhd:189); a power-of-two N_REF divides exactly by multiplication
+            const float mean = n_ref_pow2 ? (float)(s * inv_n) : (float)(s / (double)a.n_ref);
+            const float lo = __fmul_rn(0.5f, mean);
+            const float hi = __fadd_rn(mean, lo);
+            uint32_t c_gt_hi = 0u, c_lt_lo = 0u;
+            RDP_UNROLL
+            for (int q = 0; q < Sh::MAXQ; ++q) {
+                c_gt_hi += (uint32_t)__float_as_int(__fadd_rn(hi, -v[q])) >> 31;      // v > hi
+                c_lt_lo += (uint32_t)__float_as_int(__fadd_rn(v[q], -lo)) >> 31;      // v < lo (zero slots count iff lo > 0)
+            }
+            const int packed = __reduce_add_sync(0xffffffffu, (int)(c_gt_hi | (c_lt_lo << 16)));
+            const int n_le_hi = a.n_ref - (packed & 0xffff);
+            const int n_lt_lo = (packed >> 16) - (lo > 0.0f ? NZ : 0);
+            // :193-199  x_k > hi -> MAX ; x_k < lo -> MIN ; else NOM
+            scale = (n_le_hi <= a.rank_idx) ? a.smax : (n_lt_lo >= a.rank_idx + 1) ? a.smin : a.snom;
+        }
+        uint32_t c = 0u;
+        RDP_UNROLL
+        for (int q = 0; q < Sh::MAXQ; ++q) c += (uint32_t)__float_as_int(__fadd_rn(__fmul_rn(v[q], scale), -cut)) >> 31;
+        const int n_lt = __reduce_add_sync(0xffffffffu, (int)c) - NZ;       // zero slots: 0 - cut < 0 (cut > 0 here)
+        const bool det = cut > 0.0f && n_lt >= a.rank_idx + 1;             // cut > x_k * scale  (:213)
+        if (det && lane == 0) {
+            atomicOr(bits + tl * Sh::TWORDS + (tcx >> 5), 1u << (tcx & 31));
+            if (cfar_out)
+                cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)(r0 + tl) * a.n_doppler + c0 + tcx] = cut;
+        }
+    }
+    __syncthreads();
+    // bitmask of this tile: rows r0.., words (c0 / 32)..  (TCOLS is a multiple of 32 so tiles own whole words)
+    uint32_t* bm = det_bits + map * (long long)a.n_range * a.words_per_row;
+    for (int i = threadIdx.x; i < Sh::TROWS * Sh::TWORDS; i += 256) {
+        const int rl = i / Sh::TWORDS, w = i % Sh::TWORDS;
+        const int line = r0 + rl, word = c0 / 32 + w;
+        if (line < a.n_range && word < a.words_per_row) bm[(long long)line * a.words_per_row + word] = bits[i];
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // Generic kernel, geometry at run time (any window up to 32*MAXQ_GENERIC cells): one warp per
-// cell straight from global / L2.  Slow; used only for window shapes without a tiled instance.
+// 32 consecutive cells (one bitmask word) straight from global / L2.  Slow; used only for window
+// shapes without a tiled instance.
 // ------------------------------------------------------------------------------------------
 constexpr int MAXQ_GENERIC = 40;   // windows up to 1280 cells
 
 __global__ void __launch_bounds__(256)
 k3_cfar_generic_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out,
-                       rdp_det* __restrict__ dets, int* __restrict__ counts, CfarArgs a, long long n_cells) {
+                       uint32_t* __restrict__ det_bits, CfarArgs a, long long n_words) {
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const long long words_per_map = (long long)a.n_range * a.words_per_row;
     const long long cells_per_map = (long long)a.n_range * a.n_doppler;
-    for (long long cell = (long long)blockIdx.x * 8 + warp; cell < n_cells; cell += (long long)gridDim.x * 8) {
-        const long long map = cell / cells_per_map;
-        const int line = (int)((cell % cells_per_map) / a.n_doppler), col = (int)(cell % a.n_doppler);
+    for (long long w = (long long)blockIdx.x * 8 + warp; w < n_words; w += (long long)gridDim.x * 8) {
+        const long long map = w / words_per_map;
+        const int line = (int)((w % words_per_map) / a.words_per_row), word = (int)(w % a.words_per_row);
         const float* m = rd_map + map * cells_per_map;
-        const float cv = __ldg(m + (long long)line * a.n_doppler + col);
-        const bool det = cfar_exact_warp<MAXQ_GENERIC>(a, m, line, col, cv, lane);
-        if (lane == 0) {
-            if (cfar_out) cfar_out[cell] = det ? cv : 0.0f;
-            if (det) cfar_emit(a, map, line, col, cv, dets, counts);
+        uint32_t out = 0u;
+        for (int b = 0; b < 32; ++b) {
+            const int col = word * 32 + b;
+            if (col >= a.n_doppler) break;
+            const float cv = __ldg(m + (long long)line * a.n_doppler + col);
+            const bool det = cfar_exact_warp<MAXQ_GENERIC>(a, m, line, col, cv, lane);
+            if (det) out |= 1u << b;
+            if (lane == 0 && cfar_out) cfar_out[map * cells_per_map + (long long)line * a.n_doppler + col] = det ? cv : 0.0f;
         }
+        if (lane == 0) det_bits[w] = out;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Canonical order: one CTA per CPI sorts its records by (channel, range, doppler) with a
-// shared-memory bitonic network and raises the overflow bit (radar_core.vhd:447-456 analogue).
+// K4: ordered compaction, two small kernels.  k4_row_offsets: one CTA per CPI counts the set bits
+// of every range line of every channel and exclusive-scans them in (channel, range) order ->
+// per-line record offsets, the CPI's detection count and its status word.  k4_emit: one warp per
+// line writes the `r d mag` records (radar_core.vhd:396-418, TRUE coordinates) at its offset.
+// The list is canonical without a sort; records beyond max_dets are dropped (the LAST ones in
+// canonical order) and RDP_STATUS_DET_OVERFLOW is raised (status_overflow analogue, :447-456).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k4_sort_dets_kernel(rdp_det* __restrict__ dets, const int* __restrict__ counts, uint32_t* __restrict__ status,
-                    int max_dets, int pow2_cap) {
-    RDP_DYN_SMEM(smem_raw);
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    float* mags = reinterpret_cast<float*>(keys + pow2_cap);
+k4_row_offsets_kernel(const uint32_t* __restrict__ det_bits, int* __restrict__ row_off, int* __restrict__ counts,
+                      uint32_t* __restrict__ status, CfarArgs a) {
+    __shared__ int warp_sum[8];
+    __shared__ int carry_sh;
     const int cpi = blockIdx.x;
-    const int found = counts[cpi];
-    const int n = found < max_dets ? found : max_dets;
-    if (threadIdx.x == 0) status[cpi] = (found > max_dets) ? (uint32_t)RDP_STATUS_DET_OVERFLOW : 0u;
-    rdp_det* row = dets + (long long)cpi * max_dets;
-    if (n <= 1) {
-        if (n == 1 && threadIdx.x == 0) row[0].cpi = cpi;
-        return;
-    }
-    int p = 2;
-    while (p < n) p <<= 1;
-    for (int i = threadIdx.x; i < p; i += 256) {
-        if (i < n) {
-            rdp_det d = row[i];
-            keys[i] = ((unsigned long long)(unsigned)d.channel << 48) | ((unsigned long long)(unsigned)d.range << 24) |
-                      (unsigned long long)(unsigned)d.doppler;
-            mags[i] = d.mag;
-        } else {
-            keys[i] = ~0ull;
-            mags[i] = 0.0f;
-        }
-    }
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int rows = a.n_channels * a.n_range;
+    const uint32_t* bm = det_bits + (long long)cpi * rows * a.words_per_row;
+    int* off = row_off + (long long)cpi * rows;
+    if (threadIdx.x == 0) carry_sh = 0;
     __syncthreads();
-    for (int k = 2; k <= p; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < p; i += 256) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const unsigned long long ki = keys[i], kl = keys[l];
-                    if ((ki > kl) == up) {
-                        keys[i] = kl; keys[l] = ki;
-                        const float t = mags[i]; mags[i] = mags[l]; mags[l] = t;
-                    }
-                }
-            }
-            __syncthreads();
+    for (int r0 = 0; r0 < rows; r0 += 256) {
+        const int r = r0 + threadIdx.x;
+        int n = 0;
+        if (r < rows)
+            for (int w = 0; w < a.words_per_row; ++w) n += __popc(__ldg(bm + (long long)r * a.words_per_row + w));
+        int incl = n;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        int base = carry_sh;
+        for (int i = 0; i < warp; ++i) base += warp_sum[i];
+        if (r < rows) off[r] = base + incl - n;
+        __syncthreads();
+        if (threadIdx.x == 255) carry_sh = base + incl;
+        __syncthreads();
     }
-    for (int i = threadIdx.x; i < n; i += 256) {
-        const unsigned long long key = keys[i];
-        rdp_det d;
-        d.cpi = cpi;
-        d.channel = (int)(key >> 48);
-        d.range = (int)((key >> 24) & 0xffffffull);
-        d.doppler = (int)(key & 0xffffffull);
-        d.mag = mags[i];
-        row[i] = d;
+    if (threadIdx.x == 0) {
+        const int total = carry_sh;
+        counts[cpi] = total;
+        status[cpi] = total > a.max_dets ? (uint32_t)RDP_STATUS_DET_OVERFLOW : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k4_emit_kernel(const uint32_t* __restrict__ det_bits, const int* __restrict__ row_off, const float* __restrict__ rd_map,
+               rdp_det* __restrict__ dets, CfarArgs a, long long total_rows, int cpi_label_base) {
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const long long row = (long long)blockIdx.x * 8 + warp;        // over (cpi, channel, range) of this launch
+    if (row >= total_rows) return;
+    const int rows_per_cpi = a.n_channels * a.n_range;
+    const int cpi = (int)(row / rows_per_cpi), line_all = (int)(row % rows_per_cpi);
+    const uint32_t* bm = det_bits + row * a.words_per_row;
+    int base = __ldg(row_off + row);
+    rdp_det* out = dets + (long long)cpi * a.max_dets;
+    for (int w0 = 0; w0 < a.words_per_row; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t word = (w < a.words_per_row) ? __ldg(bm + w) : 0u;
+        const int n = __popc(word);
+        int incl = n;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int slot = base + incl - n;
+        base += __shfl_sync(0xffffffffu, incl, 31);
+        while (word) {
+            const int b = __ffs(word) - 1;
+            word &= word - 1;
+            if (slot < a.max_dets) {
+                const int col = w * 32 + b;
+                rdp_det d;
+                d.cpi = cpi_label_base + cpi;
+                d.channel = line_all / a.n_range;
+                d.range = line_all % a.n_range;
+                d.doppler = col;
+                d.mag = __ldg(rd_map + row * a.n_doppler + col);
+                out[slot] = d;
+            }
+            ++slot;
+        }
     }
 }
 

@@ -43,8 +43,8 @@ struct K3Launcher {
     int trows, tcols;            // 0,0 => generic kernel
     size_t smem;
     cudaError_t (*prepare)(size_t smem);
-    void (*launch)(long long grid, size_t smem, cudaStream_t st, const float* rd_map, float* cfar_out, rdp_det* dets,
-                   int* counts, CfarArgs a, int tiles_r, int tiles_c);
+    void (*launch)(long long grid, size_t smem, cudaStream_t st, const float* rd_map, float* cfar_out,
+                   uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c);
 };
 
 template <class K>
@@ -150,21 +150,21 @@ struct K3Inst {
     static cudaError_t prepare(size_t s) {
         return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>, 256, s, nullptr);
     }
-    static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out, rdp_det* dets,
-                       int* counts, CfarArgs a, int tiles_r, int tiles_c) {
-        RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>), (unsigned)grid, 256, s, st, rd_map, cfar_out, dets,
-                   counts, a, tiles_r, tiles_c);
+    static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out,
+                       uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c) {
+        RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>), (unsigned)grid, 256, s, st, rd_map, cfar_out, det_bits,
+                   a, tiles_r, tiles_c);
     }
     static K3Launcher get() { return K3Launcher{Sh::TROWS, TCOLS, Sh::smem_bytes(), &prepare, &launch}; }
 };
 struct K3Generic {
     static cudaError_t prepare(size_t) { return cudaSuccess; }
-    static void launch(long long grid, size_t, cudaStream_t st, const float* rd_map, float* cfar_out, rdp_det* dets,
-                       int* counts, CfarArgs a, int, int) {
-        long long n_cells = grid;   // grid carries the cell count for the generic kernel
-        long long blocks = (n_cells + 7) / 8;
+    static void launch(long long grid, size_t, cudaStream_t st, const float* rd_map, float* cfar_out,
+                       uint32_t* det_bits, CfarArgs a, int, int) {
+        long long n_words = grid;   // grid carries the bitmask word count for the generic kernel
+        long long blocks = (n_words + 7) / 8;
         if (blocks > 148 * 64) blocks = 148 * 64;
-        RDP_LAUNCH(k3_cfar_generic_kernel, (unsigned)blocks, 256, 0, st, rd_map, cfar_out, dets, counts, a, n_cells);
+        RDP_LAUNCH(k3_cfar_generic_kernel, (unsigned)blocks, 256, 0, st, rd_map, cfar_out, det_bits, a, n_words);
     }
     static K3Launcher get() { return K3Launcher{0, 0, 0, &prepare, &launch}; }
 };
@@ -198,6 +198,8 @@ struct rdp_handle {
     float2* x_rc = nullptr;        // [chunk][channel][range][chirp]
     float* map_scratch[2] = {nullptr, nullptr};
     void* in_stage[2] = {nullptr, nullptr};
+    uint32_t* det_bits = nullptr;  // [chunk][channel][range][words_per_row] detection bitmask
+    int* row_off = nullptr;        // [chunk][channel][range] record offset of each range line within its CPI
     int* counts = nullptr;         // [max_cpis]
     uint32_t* status = nullptr;    // [max_cpis]
     rdp_det* dets = nullptr;       // [max_cpis][max_dets]   (host path)
@@ -213,7 +215,6 @@ struct rdp_handle {
     int k1_tile_chirps = 1;
     size_t k1_smem = 0;
     CfarArgs cfar;
-    int sort_pow2 = 2;
     bool stage_timing = false;
     std::vector<StageEvent> stage_events;
     float stage_ms[4] = {0, 0, 0, 0};
@@ -305,32 +306,33 @@ int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map) {
     return launch_check(h, "k2_doppler_kernel");
 }
 
-// counts must be zeroed by the caller; cpi_base offsets the CPI index written into records
-int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp_det* dets, int* counts) {
+// K3 + K4 on n_cpi <= chunk maps-worth of CPIs: bitmask, then ordered compaction into dets / counts / status
+// (all three already offset to this chunk); cpi_label is the CPI index written into the records.
+int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp_det* dets, int* counts,
+             uint32_t* status, int cpi_label) {
     const rdp_config& c = h->cfg;
     const long long maps = (long long)n_cpi * c.n_channels;
     if (maps == 0) return RDP_OK;
     stage_begin(h, 2);
     if (h->k3.trows == 0) {
-        h->k3.launch(maps * c.n_samples * c.n_chirps, 0, h->stream, rd_map, cfar_out, dets, counts, h->cfar, 0, 0);
+        h->k3.launch(maps * c.n_samples * h->cfar.words_per_row, 0, h->stream, rd_map, cfar_out, h->det_bits, h->cfar, 0, 0);
     } else {
         const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
         const int tiles_c = (c.n_chirps + h->k3.tcols - 1) / h->k3.tcols;
-        h->k3.launch(maps * tiles_r * tiles_c, h->k3.smem, h->stream, rd_map, cfar_out, dets, counts, h->cfar,
+        h->k3.launch(maps * tiles_r * tiles_c, h->k3.smem, h->stream, rd_map, cfar_out, h->det_bits, h->cfar,
                      tiles_r, tiles_c);
     }
     stage_end(h);
-    return launch_check(h, "k3_cfar_kernel");
-}
-
-int run_sort(rdp_handle* h, rdp_det* dets, const int* counts, uint32_t* status, int n_cpi) {
-    if (n_cpi == 0) return RDP_OK;
+    int rc = launch_check(h, "k3_cfar_kernel");
+    if (rc) return rc;
     stage_begin(h, 3);
-    size_t smem = (size_t)h->sort_pow2 * (sizeof(unsigned long long) + sizeof(float));
-    RDP_LAUNCH(k4_sort_dets_kernel, n_cpi, 256, smem, h->stream, dets, counts, status, h->cfg.max_dets_per_cpi,
-               h->sort_pow2);
+    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, 256, 0, h->stream, h->det_bits, h->row_off, counts, status, h->cfar);
+    const long long total_rows = maps * c.n_samples;
+    RDP_LAUNCH(k4_emit_kernel, (unsigned)((total_rows + 7) / 8), 256, 0, h->stream, h->det_bits, h->row_off, rd_map, dets,
+               h->cfar, total_rows, cpi_label);
+    h->launches += 1;
     stage_end(h);
-    return launch_check(h, "k4_sort_dets_kernel");
+    return launch_check(h, "k4 compaction kernels");
 }
 
 __global__ void __launch_bounds__(256)
@@ -378,8 +380,8 @@ int check_cfg(const rdp_config* c) {
     if (c->mag_mode < 0 || c->mag_mode > 3) return fail(nullptr, RDP_E_INVALID, "unknown mag_mode %d", c->mag_mode);
     if (c->cfar_axes < 0 || c->cfar_axes > 1 || c->cfar_edges < 0 || c->cfar_edges > 1)
         return fail(nullptr, RDP_E_INVALID, "unknown cfar_axes / cfar_edges");
-    if (c->max_dets_per_cpi < 1 || c->max_dets_per_cpi > 8192)
-        return fail(nullptr, RDP_E_INVALID, "max_dets_per_cpi must be 1..8192");
+    if (c->max_dets_per_cpi < 1 || c->max_dets_per_cpi > (1 << 24))
+        return fail(nullptr, RDP_E_INVALID, "max_dets_per_cpi must be 1..16777216");
     if (c->max_cpis < 1) return fail(nullptr, RDP_E_INVALID, "max_cpis must be >= 1");
     if (c->chunk_cpis < 0) return fail(nullptr, RDP_E_INVALID, "chunk_cpis must be >= 0");
     return RDP_OK;
@@ -395,7 +397,7 @@ void release(rdp_handle* h) {
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
-                    h->in_stage[0], h->in_stage[1], h->counts, h->status, h->dets, h->packed, h->l2_flush};
+                    h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->counts, h->status, h->dets, h->packed, h->l2_flush};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -485,23 +487,21 @@ int init_handle(rdp_handle* h) {
     }
     a.raster = c.cfar_edges == RDP_EDGES_RASTER;
     a.max_dets = c.max_dets_per_cpi;
+    a.words_per_row = (c.n_chirps + 31) / 32;
     h->k3 = k3_for(a.half_l, a.half_c, a.guard_l, a.guard_c);
     RDP_CUDA(h, h->k3.prepare(h->k3.smem));
-    h->sort_pow2 = 2;
-    while (h->sort_pow2 < c.max_dets_per_cpi) h->sort_pow2 <<= 1;
-    {
-        size_t smem = (size_t)h->sort_pow2 * (sizeof(unsigned long long) + sizeof(float));
-        RDP_CUDA(h, prepare_kernel(k4_sort_dets_kernel, 256, smem, nullptr));
-    }
 
     // chunking: keep the range-major intermediate of one chunk L2-resident between K1 and K2
     const size_t xrc_per_cpi = cells_per_cpi(c) * sizeof(float2);
     int chunk = c.chunk_cpis;
     if (chunk == 0) {
-        size_t l2 = (size_t)prop.l2CacheSize;
-        size_t budget = l2 / 2;
+        // measured on B200 (profiles/r1_chunk_sweep.txt): launches of a few CPIs are dominated by ramp /
+        // tail effects, which cost more than keeping the intermediate L2-resident saves; size a chunk
+        // so that every kernel runs many waves, within 1 GiB of intermediate.
+        size_t budget = (size_t)1 << 30;
         chunk = (int)(budget / xrc_per_cpi);
         if (chunk < 1) chunk = 1;
+        if (chunk > 256) chunk = 256;
     }
     if (chunk > c.max_cpis) chunk = c.max_cpis;
     h->chunk = chunk;
@@ -511,6 +511,10 @@ int init_handle(rdp_handle* h) {
         rc = dev_alloc(h, &h->map_scratch[i], (size_t)chunk * cells_per_cpi(c));
         if (rc) return rc;
     }
+    rc = dev_alloc(h, &h->det_bits, (size_t)chunk * c.n_channels * c.n_samples * h->cfar.words_per_row);
+    if (rc) return rc;
+    rc = dev_alloc(h, &h->row_off, (size_t)chunk * c.n_channels * c.n_samples);
+    if (rc) return rc;
     rc = dev_alloc(h, &h->counts, (size_t)c.max_cpis);
     if (rc) return rc;
     rc = dev_alloc(h, &h->status, (size_t)c.max_cpis);
@@ -645,11 +649,16 @@ int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfa
                    int32_t* n_dets, uint32_t* status) {
     if (!h || !rd_map || !dets || !n_dets || !status || n_cpi < 0)
         return fail(h, RDP_E_INVALID, "rdp_cfar_stage: bad argument");
+    const rdp_config& c = h->cfg;
     RDP_CUDA(h, cudaSetDevice(h->device));
-    RDP_CUDA(h, cudaMemsetAsync(n_dets, 0, sizeof(int32_t) * (size_t)n_cpi, h->stream));
-    int rc = run_cfar(h, rd_map, n_cpi, cfar_out, dets, n_dets);
-    if (rc) return rc;
-    return run_sort(h, dets, n_dets, status, n_cpi);
+    const size_t cells = cells_per_cpi(c);
+    for (int base = 0; base < n_cpi; base += h->chunk) {
+        const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
+        int rc = run_cfar(h, rd_map + (size_t)base * cells, n, cfar_out ? cfar_out + (size_t)base * cells : nullptr,
+                          dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base);
+        if (rc) return rc;
+    }
+    return RDP_OK;
 }
 
 int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map, rdp_det* dets,
@@ -658,7 +667,6 @@ int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd
         return fail(h, RDP_E_INVALID, "rdp_process_device: bad argument");
     const rdp_config& c = h->cfg;
     RDP_CUDA(h, cudaSetDevice(h->device));
-    RDP_CUDA(h, cudaMemsetAsync(n_dets, 0, sizeof(int32_t) * (size_t)n_cpi, h->stream));
     const size_t cells = cells_per_cpi(c);
     const size_t in_stride = cells * in_bytes_per_sample(c);
     for (int base = 0; base < n_cpi; base += h->chunk) {
@@ -669,11 +677,10 @@ int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd
         if (rc) return rc;
         rc = run_doppler(h, h->x_rc, n, map);
         if (rc) return rc;
-        // records carry the CPI index relative to this chunk's counts/dets pointers; fix below
-        rc = run_cfar(h, map, n, nullptr, dets + (size_t)base * c.max_dets_per_cpi, n_dets + base);
+        rc = run_cfar(h, map, n, nullptr, dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base);
         if (rc) return rc;
     }
-    return run_sort(h, dets, n_dets, status, n_cpi);
+    return RDP_OK;
 }
 
 int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map, rdp_det* dets,
@@ -688,7 +695,6 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
     if (rc) return rc;
     const size_t cells = cells_per_cpi(c);
     const size_t in_stride = cells * in_bytes_per_sample(c);
-    RDP_CUDA(h, cudaMemsetAsync(h->counts, 0, sizeof(int) * (size_t)n_cpi, h->stream));
     int k = 0;
     for (int base = 0; base < n_cpi; base += h->chunk, ++k) {
         const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
@@ -705,7 +711,8 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
         if (rc) return rc;
         rc = run_doppler(h, h->x_rc, n, map);
         if (rc) return rc;
-        rc = run_cfar(h, map, n, nullptr, h->dets + (size_t)base * c.max_dets_per_cpi, h->counts + base);
+        rc = run_cfar(h, map, n, nullptr, h->dets + (size_t)base * c.max_dets_per_cpi, h->counts + base,
+                      h->status + base, base);
         if (rc) return rc;
         RDP_CUDA(h, cudaEventRecord(h->ev_done[b], h->stream));
         if (rd_map) {
@@ -715,8 +722,6 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
             RDP_CUDA(h, cudaEventRecord(h->ev_mapout[b], h->d2h_stream));
         }
     }
-    rc = run_sort(h, h->dets, h->counts, h->status, n_cpi);
-    if (rc) return rc;
     h->launches += 1;
     RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, h->dets, h->counts, h->packed, c.max_dets_per_cpi, 0);
     rc = launch_check(h, "k5_pack_dets_kernel");

@@ -349,7 +349,7 @@ class RadarCore:
         ms = (C.c_float * 4)()
         n = (C.c_int64 * 4)()
         self._check(self.lib.rdp_get_stage_timing(self.h, ms, n))
-        names = ("range", "doppler", "cfar", "sort")
+        names = ("range", "doppler", "cfar", "compact")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
 
     def flush_l2(self):

@@ -51,7 +51,8 @@ enum { RDP_EDGES_ZERO = 0, RDP_EDGES_RASTER = 1 };
 /* status word bits (one word per CPI) -- the sticky `status_overflow` of
  * rtl/src/radar_core.vhd:447-456 split by cause.                                         */
 enum {
-    RDP_STATUS_DET_OVERFLOW = 1u << 0   /* more than max_dets_per_cpi detections: list truncated */
+    RDP_STATUS_DET_OVERFLOW = 1u << 0   /* more than max_dets_per_cpi detections: the list holds the
+                                           first max_dets_per_cpi in (channel, range, doppler) order */
 };
 
 /*
@@ -79,7 +80,7 @@ typedef struct rdp_config {
     int32_t cfar_axes;         /* RDP_AXES_*                                              */
     int32_t cfar_edges;        /* RDP_EDGES_*                                             */
     float   window_gain;       /* 1.0; 2.0 mirrors the as-built x2 of window_multiplier.vhd:146-149 */
-    int32_t max_dets_per_cpi;  /* detection-list capacity per CPI (<= 8192)               */
+    int32_t max_dets_per_cpi;  /* detection-list capacity per CPI                         */
     int32_t max_cpis;          /* largest n_cpi a single rdp_process* call may pass       */
     int32_t chunk_cpis;        /* CPIs per internal pass (0 = auto: sized so the range-major
                                   intermediate stays L2-resident between the two FFT kernels) */
@@ -164,7 +165,7 @@ int rdp_copy_d2h(rdp_handle* h, void* dst_host, const void* src_device, size_t b
 int rdp_timer_start(rdp_handle* h);
 int rdp_timer_stop(rdp_handle* h, float* elapsed_ms);            /* synchronises            */
 int rdp_set_stage_timing(rdp_handle* h, int32_t enable);         /* events around each kernel */
-/* ms[0..3] = range, doppler, cfar, sort kernels; launches[0..3] likewise; resets the sums.  */
+/* ms[0..3] = range, doppler, cfar, compaction kernels; launches[0..3] likewise; resets the sums. */
 int rdp_get_stage_timing(rdp_handle* h, float ms[4], int64_t launches[4]);
 int rdp_flush_l2(rdp_handle* h);
 

@@ -58,8 +58,10 @@ def case_doppler_stage(make_core, n_samples, n_chirps, mti_mode=0, mag_mode="amb
                    window_gain=window_gain) as c:
         got = c.doppler_stage(x)
     ref = fp.doppler_stage(x, mti_mode, mag_mode, window_gain)
-    if mag_mode == "logpow":
-        assert np.abs(got - ref).max() <= 1e-3            # dB
+    if mag_mode == "logpow":                              # compare in the linear domain (dB of a null is ill-conditioned)
+        assert rel_err(10.0 ** (got.astype(np.float64) / 10.0), 10.0 ** (ref / 10.0)) <= 1e-5
+        strong = ref >= ref.max() - 60.0
+        assert np.abs(got - ref)[strong].max() <= 1e-2
     elif mag_mode == "pow":
         assert rel_err(got, ref) <= 4 * MAP_TOL
     else:
@@ -83,6 +85,7 @@ def case_cfar_stage(make_core, n_range, n_doppler, seed=1, **kw):
     """CFAR stage on an identical float32 map: the dense RTL-style output and the detection list
     must be BIT-EXACT against the oracle."""
     m = rayleigh_map(n_range, n_doppler, seed)
+    kw.setdefault("max_dets_per_cpi", 1 << 16)
     with make_core(n_range=n_range, n_doppler=n_doppler, n_channels=2, **kw) as c:
         dets, counts, status, dense = c.cfar_stage(m[None])
     okw = {k: v for k, v in kw.items() if k in fp.DEFAULTS}
@@ -113,6 +116,7 @@ def case_cfar_tb_map(make_core):
 
 def case_end_to_end(make_core, n_cpi, n_ch, n_chirps, n_samples, seed=11, fmt="int16", **kw):
     cube, _ = st.synthetic_cube(n_cpi, n_ch, n_chirps, n_samples, seed=seed, dtype=fmt)
+    kw.setdefault("max_dets_per_cpi", 1 << 18)
     with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, input_format=fmt, max_cpis=n_cpi, **kw) as c:
         rd_map, dets, n_dets, status = c.process(cube)
         launches = c.info()["kernel_launches"]
@@ -142,6 +146,10 @@ def case_overflow_flag(make_core):
         dets, counts, status, _ = c.cfar_stage(m[None], want_dense=False)
     assert counts[0] > 8 and status[0] & 1 and len(dets) == 8
     check_canonical(dets)
+    ref = fp.detections(fp.cfar_stage(m[0], scale_override=1))
+    assert counts[0] == len(ref)
+    for f in ("range", "doppler", "mag"):                 # truncation keeps the FIRST records in canonical order
+        assert np.array_equal(dets[f], ref[f][:8])
 
 
 def case_chunking_invariance(make_core, n_samples=64, n_chirps=32):
