@@ -35,6 +35,7 @@ struct dim3 {
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct uint2 { unsigned x, y; };
+struct alignas(8) int2 { int x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct short2 { short x, y; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }

@@ -23,10 +23,30 @@ struct K1Shape {
     }
 };
 
-__device__ __forceinline__ float2 load_sample_i16(const uint32_t* __restrict__ p, long long idx) {
-    uint32_t w = __ldg(p + idx);                           // {Q[31:16], I[15:0]}  window_multiplier.vhd:93-94
-    return make_float2((float)(short)(w & 0xffffu), (float)((int)w >> 16));
-}
+// raw sample word(s) of one thread for one chirp: int16 IQ = one 32-bit word {Q[31:16], I[15:0]}
+// (window_multiplier.vhd:93-94), complex64 = one float2
+template <int IN_FMT>
+struct K1Raw;
+template <>
+struct K1Raw<0> {
+    typedef uint32_t T;
+    static __device__ __forceinline__ T zero() { return 0u; }
+    static __device__ __forceinline__ T load(const void* __restrict__ cube, long long idx) {
+        return __ldg(reinterpret_cast<const uint32_t*>(cube) + idx);
+    }
+    static __device__ __forceinline__ float2 cvt(T w) {
+        return make_float2((float)(short)(w & 0xffffu), (float)((int)w >> 16));
+    }
+};
+template <>
+struct K1Raw<1> {
+    typedef float2 T;
+    static __device__ __forceinline__ T zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ T load(const void* __restrict__ cube, long long idx) {
+        return __ldg(reinterpret_cast<const float2*>(cube) + idx);
+    }
+    static __device__ __forceinline__ float2 cvt(T w) { return w; }
+};
 
 template <class Plan, int IN_FMT>
 __global__ void __launch_bounds__(K1Shape<Plan>::THREADS)
@@ -34,9 +54,10 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
                 const float* __restrict__ window, const float2* __restrict__ twtab,
                 int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles) {
     constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
-    constexpr int G = K1Shape<Plan>::G, THREADS = K1Shape<Plan>::THREADS;
+    constexpr int G = K1Shape<Plan>::G, THREADS = K1Shape<Plan>::THREADS, TCM = K1Shape<Plan>::TC_MAX;
     using P0 = typename Plan::P0;
     using PL = typename Plan::LAST;
+    using Raw = K1Raw<IN_FMT>;
     RDP_DYN_SMEM(smem_raw);
     float2* tile = reinterpret_cast<float2*>(smem_raw);
     const int tcp = tile_chirps + 1;                       // +1 complex: conflict-free column writes
@@ -54,6 +75,24 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
     int parity = 0;
     const int iters = (tile_chirps + G - 1) / G;
 
+    // software pipeline: the raw samples of the NEXT chirp this group transforms are in flight while the
+    // current one is in the butterflies
+    typename Raw::T raw[E];
+    auto fetch = [&](long long t, int it) {
+        const int c = it * G + gid;
+        const bool ok = t < total_tiles && c < tile_chirps;
+        const long long map = t / tiles_per_map;
+        const int c0 = (int)(t % tiles_per_map) * tile_chirps;
+        const long long base = ((map * n_chirps) + c0 + c) * (long long)N;
+        RDP_UNROLL
+        for (int b = 0; b < P0::NB; ++b) {
+            RDP_UNROLL
+            for (int r = 0; r < P0::R; ++r)
+                raw[b * P0::R + r] = ok ? Raw::load(cube, base + P0::in_index(tid, b, r)) : Raw::zero();
+        }
+    };
+    fetch(blockIdx.x, 0);
+
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const long long map = t / tiles_per_map;
         const int c0 = (int)(t % tiles_per_map) * tile_chirps;
@@ -61,21 +100,13 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
             const int c = it * G + gid;
             const bool active = c < tile_chirps;
             float2 v[E];
-            const long long base = ((map * n_chirps) + c0 + c) * (long long)N;
             RDP_UNROLL
-            for (int b = 0; b < P0::NB; ++b) {
-                RDP_UNROLL
-                for (int r = 0; r < P0::R; ++r) {
-                    float2 s = make_float2(0.f, 0.f);
-                    if (active) {
-                        const long long idx = base + P0::in_index(tid, b, r);
-                        if (IN_FMT == 0) s = load_sample_i16(reinterpret_cast<const uint32_t*>(cube), idx);
-                        else s = __ldg(reinterpret_cast<const float2*>(cube) + idx);
-                    }
-                    const float w = wv[b * P0::R + r];
-                    v[b * P0::R + r] = make_float2(s.x * w, s.y * w);
-                }
+            for (int i = 0; i < E; ++i) {
+                const float2 s = Raw::cvt(raw[i]);
+                v[i] = make_float2(s.x * wv[i], s.y * wv[i]);
             }
+            if (it + 1 < iters) fetch(t, it + 1);
+            else fetch(t + gridDim.x, 0);
             Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
             if (active) {
                 RDP_UNROLL
@@ -88,10 +119,16 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
         __syncthreads();
         // range-major store: row k of the tile -> x_rc[map][k][c0 .. c0+tile_chirps)
         float2* dst = x_rc + map * (long long)N * n_chirps + c0;
-        const int total = N * tile_chirps;
-        for (int i = threadIdx.x; i < total; i += THREADS) {
-            const int k = i / tile_chirps, c = i % tile_chirps;
-            dst[(long long)k * n_chirps + c] = tile[k * tcp + c];
+        if (tile_chirps == TCM) {                          // compile-time tile width: no integer division
+            const int c = threadIdx.x % TCM;
+            for (int k = threadIdx.x / TCM; k < N; k += THREADS / TCM)
+                dst[(long long)k * n_chirps + c] = tile[k * (TCM + 1) + c];
+        } else {
+            const int total = N * tile_chirps;
+            for (int i = threadIdx.x; i < total; i += THREADS) {
+                const int k = i / tile_chirps, c = i % tile_chirps;
+                dst[(long long)k * n_chirps + c] = tile[k * tcp + c];
+            }
         }
         __syncthreads();
     }

@@ -54,34 +54,50 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
         for (int r = 0; r < P0::R; ++r) wv[b * P0::R + r] = __ldg(window + P0::in_index(tid, b, r));
     }
     int parity = 0;
+    const long long stride = (long long)gridDim.x * G;
 
-    for (long long row0 = (long long)blockIdx.x * G; row0 < n_rows; row0 += (long long)gridDim.x * G) {
-        const long long row = row0 + gid;
-        const bool active = row < n_rows;
+    // software pipeline: the next range line's samples are in flight during the butterflies
+    float2 raw[E];
+    auto fetch = [&](long long row) {
+        const bool ok = row < n_rows;
         const float2* src = x_rc + row * N;
-        float2 v[E];
         RDP_UNROLL
         for (int b = 0; b < P0::NB; ++b) {
             RDP_UNROLL
-            for (int r = 0; r < P0::R; ++r) {
-                const int n = P0::in_index(tid, b, r);
-                float2 s = make_float2(0.f, 0.f);
-                if (active) {
-                    s = __ldg(src + n);
-                    if (mti_mode != 0) {                 // doppler_notch.vhd:72-93, zero initial state (:99-102)
-                        float2 d1 = (n >= 1) ? __ldg(src + n - 1) : make_float2(0.f, 0.f);
-                        if (mti_mode == 2) {
-                            s = csub(s, d1);
-                        } else {
-                            float2 d2 = (n >= 2) ? __ldg(src + n - 2) : make_float2(0.f, 0.f);
-                            s = make_float2(s.x - 2.0f * d1.x + d2.x, s.y - 2.0f * d1.y + d2.y);
-                        }
+            for (int r = 0; r < P0::R; ++r)
+                raw[b * P0::R + r] = ok ? __ldg(src + P0::in_index(tid, b, r)) : make_float2(0.f, 0.f);
+        }
+    };
+    fetch((long long)blockIdx.x * G + gid);
+
+    for (long long row0 = (long long)blockIdx.x * G; row0 < n_rows; row0 += stride) {
+        const long long row = row0 + gid;
+        const bool active = row < n_rows;
+        float2 v[E];
+        if (mti_mode == 0) {
+            RDP_UNROLL
+            for (int i = 0; i < E; ++i) v[i] = make_float2(raw[i].x * wv[i], raw[i].y * wv[i]);
+        } else {                                         // doppler_notch.vhd:72-93, zero initial state (:99-102)
+            const float2* src = x_rc + row * N;
+            RDP_UNROLL
+            for (int b = 0; b < P0::NB; ++b) {
+                RDP_UNROLL
+                for (int r = 0; r < P0::R; ++r) {
+                    const int n = P0::in_index(tid, b, r);
+                    float2 s = raw[b * P0::R + r];
+                    const float2 d1 = (active && n >= 1) ? __ldg(src + n - 1) : make_float2(0.f, 0.f);
+                    if (mti_mode == 2) {
+                        s = csub(s, d1);
+                    } else {
+                        const float2 d2 = (active && n >= 2) ? __ldg(src + n - 2) : make_float2(0.f, 0.f);
+                        s = make_float2(s.x - 2.0f * d1.x + d2.x, s.y - 2.0f * d1.y + d2.y);
                     }
+                    const float w = wv[b * P0::R + r];
+                    v[b * P0::R + r] = make_float2(s.x * w, s.y * w);
                 }
-                const float w = wv[b * P0::R + r];
-                v[b * P0::R + r] = make_float2(s.x * w, s.y * w);
             }
         }
+        fetch(row + stride);
         Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
         if (active) {
             float* dst = rd_map + row * N;

@@ -125,8 +125,14 @@ struct K3Shape {
     static constexpr int WIN = (2 * HL + 1) * (2 * HC + 1);
     static constexpr int MAXQ = (WIN + 31) / 32;
     static constexpr int TWORDS = (TCOLS + 31) / 32;              // bitmask words per tile row
+    static constexpr int NREF = WIN - (2 * GL + 1) * (2 * GC + 1);
+    // phase 2: G lanes per survivor (32 / G survivors per warp pass), NQ window slots per lane
+    static constexpr int G = WIN <= 160 ? 8 : (WIN <= 320 ? 16 : 32);
+    static constexpr int NQ = (WIN + G - 1) / G, NSLOT = NQ * G, NZ = NSLOT - NREF;
+    static constexpr int TF_WORDS = SROWS * SCOLS + 4;            // + a cell that always reads 0.0f
+    static constexpr int ZERO_IDX = SROWS * SCOLS;
     static constexpr size_t smem_bytes() {
-        return sizeof(float) * 2 * SROWS * SCOLS + sizeof(int) * (TROWS * TCOLS + TROWS * TWORDS + 4);
+        return sizeof(float) * (TF_WORDS + SROWS * SCOLS) + sizeof(int) * (TROWS * TCOLS + TROWS * TWORDS + 4 + 2 * NSLOT);
     }
 };
 
@@ -168,10 +174,11 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
     RDP_DYN_SMEM(smem_raw);
     float* tf = reinterpret_cast<float*>(smem_raw);                           // raw magnitudes
-    uint32_t* th = reinterpret_cast<uint32_t*>(tf + Sh::SROWS * Sh::SCOLS);   // bf16x2 (lo, lo) of fl(v*s1)
+    uint32_t* th = reinterpret_cast<uint32_t*>(tf + Sh::TF_WORDS);            // bf16x2 (lo, lo) of fl(v*s1)
     int* surv = reinterpret_cast<int*>(th + Sh::SROWS * Sh::SCOLS);
     uint32_t* bits = reinterpret_cast<uint32_t*>(surv + Sh::TROWS * TCOLS);
     int* n_surv = reinterpret_cast<int*>(bits + Sh::TROWS * Sh::TWORDS);
+    int* wtab = n_surv + 4;                                                   // [NSLOT][2]: tf index = ctr * mul + add
 
     const long long tile_id = blockIdx.x;
     const long long map = tile_id / (tiles_r * tiles_c);
@@ -179,8 +186,17 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     const int r0 = tr * Sh::TROWS, c0 = tc * TCOLS;
     const float* m = rd_map + map * (long long)a.n_range * a.n_doppler;
 
-    if (threadIdx.x == 0) *n_surv = 0;
+    if (threadIdx.x == 0) {
+        *n_surv = 0;
+        tf[Sh::ZERO_IDX] = 0.0f;
+    }
     for (int i = threadIdx.x; i < Sh::TROWS * Sh::TWORDS; i += 256) bits[i] = 0u;
+    for (int sl = threadIdx.x; sl < Sh::NSLOT; sl += 256) {       // window slot -> reference cell, or the zero cell
+        const int dl = sl / (2 * HC + 1) - HL, dc = sl % (2 * HC + 1) - HC;
+        const bool ref = sl < Sh::WIN && !(dl >= -GL && dl <= GL && dc >= -GC && dc <= GC);
+        wtab[2 * sl] = ref ? 1 : 0;
+        wtab[2 * sl + 1] = ref ? dl * Sh::SCOLS + dc : Sh::ZERO_IDX;
+    }
     {   // tile + halo, one warp per tile row (coalesced, no per-element index arithmetic)
         const int lw = threadIdx.x / 32, ll = threadIdx.x % 32;
         for (int lr = lw; lr < Sh::SROWS; lr += 8) {
@@ -243,62 +259,61 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     }
     __syncthreads();
 
-    // ---- phase 2: exact decision, one warp per survivor, from the raw tile ----------------------------
-    // Window slots are dealt to lanes (slot = lane + 32 q); guard / padding slots read as 0 and their known
-    // contribution to each count is subtracted.  Counting uses the sign bit of an exact float subtraction.
+    // ---- phase 2: exact decision from the raw tile: G lanes per survivor, 32/G survivors per warp pass ---
+    // Window slots are dealt to the G lanes (slot = sub + G q); guard / padding slots read the zero cell and
+    // their known contribution to each count is subtracted.  Counting = sign bit of an exact float subtraction.
     const int ns = *n_surv;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    constexpr int NZ = 32 * Sh::MAXQ - (Sh::WIN - (2 * GL + 1) * (2 * GC + 1));     // non-reference slots per warp
-    int off[Sh::MAXQ];
-    bool isref[Sh::MAXQ];
-    RDP_UNROLL
-    for (int q = 0; q < Sh::MAXQ; ++q) {
-        const int idx = lane + 32 * q;
-        const int dl = idx / (2 * HC + 1) - HL, dc = idx % (2 * HC + 1) - HC;
-        isref[q] = idx < Sh::WIN && !(dl >= -GL && dl <= GL && dc >= -GC && dc <= GC);
-        off[q] = isref[q] ? dl * Sh::SCOLS + dc : 0;
-    }
+    constexpr int G = Sh::G, NQ = Sh::NQ, NZ = Sh::NZ;
+    const int sub = lane % G, grp = lane / G;
     const bool n_ref_pow2 = (a.n_ref & (a.n_ref - 1)) == 0;
     const double inv_n = 1.0 / (double)a.n_ref;
-    for (int i = warp; i < ns; i += 8) {
-        const int code = surv[i];
+    for (int i0 = warp * (32 / G); i0 < ns; i0 += 8 * (32 / G)) {
+        const int i = i0 + grp;
+        const bool valid = i < ns;
+        const int code = valid ? surv[i] : 0;                      // idle groups chew on tile cell (0, 0)
         const int tl = code >> 16, tcx = code & 0xffff;
-        const float* ctr = tf + (tl + HL) * Sh::SCOLS + tcx + HC;
-        const float cut = *ctr;
-        float v[Sh::MAXQ];
+        const int cidx = (tl + HL) * Sh::SCOLS + tcx + HC;
+        const float cut = tf[cidx];
+        float v[NQ];
         RDP_UNROLL
-        for (int q = 0; q < Sh::MAXQ; ++q) {
-            const float t = ctr[off[q]];
-            v[q] = isref[q] ? t : 0.0f;
+        for (int q = 0; q < NQ; ++q) {
+            const int2 w = *reinterpret_cast<const int2*>(wtab + 2 * (q * G + sub));
+            v[q] = tf[cidx * w.x + w.y];
         }
         float scale = a.s1;
         if (a.adaptive) {
             double s = 0.0;
             RDP_UNROLL
-            for (int q = 0; q < Sh::MAXQ; ++q) s += (double)v[q];
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            for (int q = 0; q < NQ; ++q) s += (double)v[q];
+            RDP_UNROLL
+            for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             // mean = float32(S / N_REF)  (os_cfar_2d.vhd:189); a power-of-two N_REF divides exactly by multiplication
             const float mean = n_ref_pow2 ? (float)(s * inv_n) : (float)(s / (double)a.n_ref);
             const float lo = __fmul_rn(0.5f, mean);
             const float hi = __fadd_rn(mean, lo);
             uint32_t c_gt_hi = 0u, c_lt_lo = 0u;
             RDP_UNROLL
-            for (int q = 0; q < Sh::MAXQ; ++q) {
+            for (int q = 0; q < NQ; ++q) {
                 c_gt_hi += (uint32_t)__float_as_int(__fadd_rn(hi, -v[q])) >> 31;      // v > hi
                 c_lt_lo += (uint32_t)__float_as_int(__fadd_rn(v[q], -lo)) >> 31;      // v < lo (zero slots count iff lo > 0)
             }
-            const int packed = __reduce_add_sync(0xffffffffu, (int)(c_gt_hi | (c_lt_lo << 16)));
+            int packed = (int)(c_gt_hi | (c_lt_lo << 16));
+            RDP_UNROLL
+            for (int o = G / 2; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
             const int n_le_hi = a.n_ref - (packed & 0xffff);
             const int n_lt_lo = (packed >> 16) - (lo > 0.0f ? NZ : 0);
             // :193-199  x_k > hi -> MAX ; x_k < lo -> MIN ; else NOM
             scale = (n_le_hi <= a.rank_idx) ? a.smax : (n_lt_lo >= a.rank_idx + 1) ? a.smin : a.snom;
         }
-        uint32_t c = 0u;
+        int c = 0;
         RDP_UNROLL
-        for (int q = 0; q < Sh::MAXQ; ++q) c += (uint32_t)__float_as_int(__fadd_rn(__fmul_rn(v[q], scale), -cut)) >> 31;
-        const int n_lt = __reduce_add_sync(0xffffffffu, (int)c) - NZ;       // zero slots: 0 - cut < 0 (cut > 0 here)
-        const bool det = cut > 0.0f && n_lt >= a.rank_idx + 1;             // cut > x_k * scale  (:213)
-        if (det && lane == 0) {
+        for (int q = 0; q < NQ; ++q) c += (int)((uint32_t)__float_as_int(__fadd_rn(__fmul_rn(v[q], scale), -cut)) >> 31);
+        RDP_UNROLL
+        for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        const int n_lt = c - NZ;                                   // zero slots: 0 - cut < 0 (cut > 0 here)
+        const bool det = valid && cut > 0.0f && n_lt >= a.rank_idx + 1;   // cut > x_k * scale  (:213)
+        if (det && sub == 0) {
             atomicOr(bits + tl * Sh::TWORDS + (tcx >> 5), 1u << (tcx & 31));
             if (cfar_out)
                 cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)(r0 + tl) * a.n_doppler + c0 + tcx] = cut;

@@ -173,6 +173,7 @@ class RadarCore:
         self.input_format = input_format
         self.max_dets_per_cpi, self.max_cpis = max_dets_per_cpi, max_cpis
         self._pinned = []
+        self._out = {}           # page-locked result buffers of process(), reused between calls
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc):
@@ -181,6 +182,7 @@ class RadarCore:
 
     def close(self):
         if getattr(self, "h", None):
+            self._out = {}
             for p in self._pinned:
                 self.lib.rdp_host_free(self.h, p)
             self._pinned = []
@@ -257,21 +259,32 @@ class RadarCore:
         return np.ascontiguousarray(cube).reshape(lead + tail)
 
     # -- the path ---------------------------------------------------------------------------
+    def _out_buffer(self, name, shape, dtype):
+        """Page-locked result buffer, (re)allocated only when it has to grow."""
+        n = int(np.prod(shape))
+        cur = self._out.get(name)
+        if cur is None or cur.size < n or cur.dtype != np.dtype(dtype):
+            cur = self.pinned_empty((max(n, 1),), dtype)
+            self._out[name] = cur
+        return cur[:n].reshape(shape)
+
     def process(self, cube: np.ndarray, want_map: bool = True):
         """HOST buffers in, HOST results out (rdp_process_host).
         Returns (rd_map float32 [cpi, channel, range, doppler] or None,
                  detections DET_DTYPE in canonical (cpi, channel, range, doppler) order,
-                 n_dets int32 [cpi] (as found; > max_dets_per_cpi means truncated), status uint32 [cpi])."""
+                 n_dets int32 [cpi] (as found; > max_dets_per_cpi means truncated), status uint32 [cpi]).
+        The arrays are views of page-locked buffers owned by this object: valid until the next
+        process() call (copy them to keep them)."""
         cube = self._as_cube(cube)
         n_cpi = cube.shape[0]
-        rd_map = np.empty((n_cpi, self.n_channels, self.n_range, self.n_doppler), np.float32) if want_map else None
-        dets = np.empty(n_cpi * self.max_dets_per_cpi, dtype=DET_DTYPE)
-        n_dets = np.zeros(n_cpi, np.int32)
-        status = np.zeros(n_cpi, np.uint32)
+        rd_map = self._out_buffer("map", (n_cpi, self.n_channels, self.n_range, self.n_doppler), np.float32) if want_map else None
+        dets = self._out_buffer("dets", (n_cpi * self.max_dets_per_cpi,), DET_DTYPE)
+        n_dets = self._out_buffer("n_dets", (n_cpi,), np.int32)
+        status = self._out_buffer("status", (n_cpi,), np.uint32)
         self._check(self.lib.rdp_process_host(self.h, _ptr(cube), n_cpi, _ptr(rd_map) if want_map else None,
                                               _ptr(dets), _ptr(n_dets), _ptr(status)))
         total = int(np.minimum(n_dets, self.max_dets_per_cpi).sum())
-        return rd_map, dets[:total].copy(), n_dets, status
+        return rd_map, dets[:total], n_dets, status
 
     def process_device(self, d_cube: DeviceBuffer, n_cpi: int, d_map: DeviceBuffer | None,
                        d_dets: DeviceBuffer, d_counts: DeviceBuffer, d_status: DeviceBuffer):
@@ -379,7 +392,7 @@ def process_cpi(frame: np.ndarray, **kw):
         frame = frame.astype(np.complex64, copy=False)
     with _core_for(frame, False, kw) as core:
         m, dets, _, _ = core.process(frame)
-    return m[0], dets
+        return m[0].copy(), dets.copy()
 
 
 def process_batch(cubes: np.ndarray, **kw):
@@ -389,4 +402,4 @@ def process_batch(cubes: np.ndarray, **kw):
         cubes = cubes.astype(np.complex64, copy=False)
     with _core_for(cubes, True, kw) as core:
         m, dets, counts, _ = core.process(cubes)
-    return m, dets, counts
+        return m.copy(), dets.copy(), counts.copy()

@@ -118,7 +118,7 @@ def case_end_to_end(make_core, n_cpi, n_ch, n_chirps, n_samples, seed=11, fmt="i
     cube, _ = st.synthetic_cube(n_cpi, n_ch, n_chirps, n_samples, seed=seed, dtype=fmt)
     kw.setdefault("max_dets_per_cpi", 1 << 18)
     with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, input_format=fmt, max_cpis=n_cpi, **kw) as c:
-        rd_map, dets, n_dets, status = c.process(cube)
+        rd_map, dets, n_dets, status = (x.copy() for x in c.process(cube))
         launches = c.info()["kernel_launches"]
     okw = {k: v for k, v in kw.items() if k in fp.DEFAULTS}
     ref_map, ref_dets, ref_counts = fp.process_batch(cube, **okw)
@@ -158,7 +158,7 @@ def case_chunking_invariance(make_core, n_samples=64, n_chirps=32):
     for chunk in (1, 2, 3):
         with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=2, max_cpis=3, chunk_cpis=chunk) as c:
             assert c.info()["chunk_cpis"] == chunk
-            out.append(c.process(cube))
+            out.append(tuple(x.copy() for x in c.process(cube)))
     for o in out[1:]:
         assert np.array_equal(o[0], out[0][0])
         assert np.array_equal(o[1], out[0][1]) and np.array_equal(o[2], out[0][2])
@@ -172,7 +172,7 @@ def case_golden_chirp(make_core, golden_chirp_1024, n_chirps=16):
     z = 0.5 * base[None, :] * ramp
     cube = np.stack([np.round(z.real), np.round(z.imag)], axis=-1).astype(np.int16)
     with make_core(n_range=1024, n_doppler=n_chirps) as c:
-        rd_map, dets, n_dets, status = c.process(cube)
+        rd_map, dets, n_dets, status = (x.copy() for x in c.process(cube))
     ref_map, ref_dets = fp.process_cpi(cube)
     r, d = np.unravel_index(np.argmax(rd_map[0, 0]), rd_map[0, 0].shape)
     assert (int(r), int(d)) == (290, 3)
