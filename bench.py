@@ -292,7 +292,7 @@ def main():
                            "unique_cpis": int(uniq.shape[0]), "chunk_cpis": info["chunk_cpis"],
                            "cfar": "ref 4/4 guard 2/1 rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
                            "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),
-                           "device": info["device_name"], "sharding": "CPIs dealt to ranks, no data-path collective"},
+                           "device": info["device_name"], "cfar_tile_staging": "TMA" if core.info()["cfar_tma"] else "manual", "sharding": "CPIs dealt to ranks, no data-path collective"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu,
                 "detections_per_cpi_mean": float(counts.mean()), "status_or": int(np.bitwise_or.reduce(status))}

@@ -121,7 +121,12 @@ template <int HL, int HC, int GL, int GC, int S, int TCOLS>
 struct K3Shape {
     static constexpr int THREADS = 256;
     static constexpr int TROWS = (THREADS / TCOLS) * S;
-    static constexpr int SROWS = TROWS + 2 * HL, SCOLS = TCOLS + 2 * HC;
+    static constexpr int SROWS = TROWS + 2 * HL;
+    // TMA needs the box to START on a 16-byte boundary in the innermost dimension (an unaligned start
+    // coordinate traps with "illegal instruction", tools/microbench/mb_tma_probe.cu), so the column halo is
+    // padded to a multiple of 4 floats on both sides: tile column c sits at shared column c + HCP
+    static constexpr int HCP = (HC + 3) / 4 * 4;
+    static constexpr int SCOLS = TCOLS + 2 * HCP;
     static constexpr int WIN = (2 * HL + 1) * (2 * HC + 1);
     static constexpr int MAXQ = (WIN + 31) / 32;
     static constexpr int TWORDS = (TCOLS + 31) / 32;              // bitmask words per tile row
@@ -129,12 +134,46 @@ struct K3Shape {
     // phase 2: G lanes per survivor (32 / G survivors per warp pass), NQ window slots per lane
     static constexpr int G = WIN <= 160 ? 8 : (WIN <= 320 ? 16 : 32);
     static constexpr int NQ = (WIN + G - 1) / G, NSLOT = NQ * G, NZ = NSLOT - NREF;
-    static constexpr int TF_WORDS = SROWS * SCOLS + 4;            // + a cell that always reads 0.0f
+    static constexpr int TF_WORDS = (SROWS * SCOLS + 4 + 31) / 32 * 32;   // one raw stage (+ a cell that reads 0.0f), 128 B multiple
     static constexpr int ZERO_IDX = SROWS * SCOLS;
+    static constexpr int TILE_BYTES = SROWS * SCOLS * 4;
     static constexpr size_t smem_bytes() {
-        return sizeof(float) * (TF_WORDS + SROWS * SCOLS) + sizeof(int) * (TROWS * TCOLS + TROWS * TWORDS + 4 + 2 * NSLOT);
+        return sizeof(float) * (2 * TF_WORDS + SROWS * SCOLS) +
+               sizeof(int) * (TROWS * TCOLS + TROWS * TWORDS + 4 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
     }
 };
+
+
+#ifdef RDP_EMU
+struct CUtensorMap_st { alignas(64) unsigned char opaque[128]; };
+typedef CUtensorMap_st CUtensorMap;
+#define RDP_GRID_CONSTANT
+#else
+#include <cuda.h>          // CUtensorMap (type only; nothing from libcuda is linked)
+#define RDP_GRID_CONSTANT __grid_constant__
+// mbarrier + TMA (cp.async.bulk.tensor) primitives, sm_90+ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tiled TMA load global -> shared; out-of-bounds elements are written as 0 (== cfar_edges ZERO)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, unsigned long long* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+#endif
 
 // one packed compare for cells (2p, 2p+1) of the strip against tile row lr, if either is a reference
 template <int HL, int GL, bool GUARD_COL, int P, int LR>
@@ -169,34 +208,76 @@ struct K3Rows<HL, GL, GUARD_COL, NROWS, NROWS> {
 template <int HL, int HC, int GL, int GC, int S, int TCOLS>
 __global__ void __launch_bounds__(256)
 k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, uint32_t* __restrict__ det_bits,
-               CfarArgs a, int tiles_r, int tiles_c) {
+               CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
+               const RDP_GRID_CONSTANT CUtensorMap tmap) {
     static_assert(S == 8, "the strip is four packed pairs");
     using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
     RDP_DYN_SMEM(smem_raw);
-    float* tf = reinterpret_cast<float*>(smem_raw);                           // raw magnitudes
-    uint32_t* th = reinterpret_cast<uint32_t*>(tf + Sh::TF_WORDS);            // bf16x2 (lo, lo) of fl(v*s1)
+    // 128-byte aligned carve-up: [2 raw stages][packed tile][survivors][bitmask][counter][window table][mbarriers]
+    unsigned char* smem_al = smem_raw + ((128 - ((uintptr_t)smem_raw & 127)) & 127);
+    float* tf0 = reinterpret_cast<float*>(smem_al);                            // raw magnitudes, two stages
+    uint32_t* th = reinterpret_cast<uint32_t*>(tf0 + 2 * Sh::TF_WORDS);        // bf16x2 (lo, lo) of fl(v*s1)
     int* surv = reinterpret_cast<int*>(th + Sh::SROWS * Sh::SCOLS);
     uint32_t* bits = reinterpret_cast<uint32_t*>(surv + Sh::TROWS * TCOLS);
     int* n_surv = reinterpret_cast<int*>(bits + Sh::TROWS * Sh::TWORDS);
-    int* wtab = n_surv + 4;                                                   // [NSLOT][2]: tf index = ctr * mul + add
-
-    const long long tile_id = blockIdx.x;
-    const long long map = tile_id / (tiles_r * tiles_c);
-    const int tr = (int)(tile_id % (tiles_r * tiles_c)) / tiles_c, tc = (int)(tile_id % tiles_c);
-    const int r0 = tr * Sh::TROWS, c0 = tc * TCOLS;
-    const float* m = rd_map + map * (long long)a.n_range * a.n_doppler;
+    int* wtab = n_surv + 4;                                                    // [NSLOT][2]: tf index = ctr * mul + add
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wtab + 2 * Sh::NSLOT);
+    const int tiles_per_map = tiles_r * tiles_c;
 
     if (threadIdx.x == 0) {
-        *n_surv = 0;
-        tf[Sh::ZERO_IDX] = 0.0f;
+        tf0[Sh::ZERO_IDX] = 0.0f;
+        tf0[Sh::TF_WORDS + Sh::ZERO_IDX] = 0.0f;
+#ifndef RDP_EMU
+        if (use_tma) {
+            mbar_init(mbar, 1);
+            mbar_init(mbar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+#endif
     }
-    for (int i = threadIdx.x; i < Sh::TROWS * Sh::TWORDS; i += 256) bits[i] = 0u;
     for (int sl = threadIdx.x; sl < Sh::NSLOT; sl += 256) {       // window slot -> reference cell, or the zero cell
         const int dl = sl / (2 * HC + 1) - HL, dc = sl % (2 * HC + 1) - HC;
         const bool ref = sl < Sh::WIN && !(dl >= -GL && dl <= GL && dc >= -GC && dc <= GC);
         wtab[2 * sl] = ref ? 1 : 0;
         wtab[2 * sl + 1] = ref ? dl * Sh::SCOLS + dc : Sh::ZERO_IDX;
     }
+    __syncthreads();
+#ifndef RDP_EMU
+    // TMA producer: the (tile + halo) box of tile `t` into raw stage `st`; coordinates may be negative /
+    // past the edge -- the hardware zero-fills, which is exactly cfar_edges = ZERO
+    const CUtensorMap* tmap_ptr = &tmap;                   // address of the __grid_constant__ parameter itself
+    auto issue = [=](long long t, int st) {
+        const long long mp = t / tiles_per_map;
+        const int rem = (int)(t % tiles_per_map);
+        mbar_expect_tx(mbar + st, (uint32_t)Sh::TILE_BYTES);
+        tma_load_3d(tf0 + st * Sh::TF_WORDS, tmap_ptr, mbar + st, (rem % tiles_c) * TCOLS - Sh::HCP, (rem / tiles_c) * Sh::TROWS - HL, (int)mp);
+    };
+    if (use_tma && threadIdx.x == 0 && (long long)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+#endif
+
+    int iter = 0;
+    for (long long tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x, ++iter) {
+    const int stage = use_tma ? (iter & 1) : 0;
+    float* tf = tf0 + stage * Sh::TF_WORDS;
+    const long long map = tile_id / tiles_per_map;
+    const int tr = (int)(tile_id % tiles_per_map) / tiles_c, tc = (int)(tile_id % tiles_c);
+    const int r0 = tr * Sh::TROWS, c0 = tc * TCOLS;
+    const float* m = rd_map + map * (long long)a.n_range * a.n_doppler;
+
+    if (threadIdx.x == 0) *n_surv = 0;
+    for (int i = threadIdx.x; i < Sh::TROWS * Sh::TWORDS; i += 256) bits[i] = 0u;
+#ifndef RDP_EMU
+    if (use_tma) {
+        // prefetch the next tile into the other stage (its previous readers finished before the barrier that
+        // ended the previous iteration), then wait for this tile's bytes
+        if (threadIdx.x == 0 && tile_id + gridDim.x < n_tiles) issue(tile_id + gridDim.x, stage ^ 1);
+        mbar_wait(mbar + stage, (uint32_t)((iter >> 1) & 1));
+        for (int i = threadIdx.x; i < Sh::SROWS * Sh::SCOLS; i += 256) {
+            const uint32_t lo = bf16_down(__fmul_rn(tf[i], a.s1));
+            th[i] = lo | (lo << 16);
+        }
+    } else
+#endif
     {   // tile + halo, one warp per tile row (coalesced, no per-element index arithmetic)
         const int lw = threadIdx.x / 32, ll = threadIdx.x % 32;
         for (int lr = lw; lr < Sh::SROWS; lr += 8) {
@@ -207,7 +288,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             for (int k = 0; k < (Sh::SCOLS + 31) / 32; ++k) {
                 const int lc = ll + 32 * k;
                 if (lc < Sh::SCOLS) {
-                    const int c = c0 - HC + lc;
+                    const int c = c0 - Sh::HCP + lc;
                     float v = 0.0f;
                     if (a.raster) {
                         const long long flat = row_base + c;
@@ -231,8 +312,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     bool force[S];
     RDP_UNROLL
     for (int p = 0; p < 4; ++p) {
-        const float c_lo = tf[(ty * S + 2 * p + HL) * Sh::SCOLS + tx + HC];
-        const float c_hi = tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + HC];
+        const float c_lo = tf[(ty * S + 2 * p + HL) * Sh::SCOLS + tx + Sh::HCP];
+        const float c_hi = tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + Sh::HCP];
         const uint32_t h0 = bf16_up(c_lo), h1 = bf16_up(c_hi);
         cb[p] = h0 | (h1 << 16);
         cl[p] = h0;
@@ -242,7 +323,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         force[2 * p] = c_lo > 0.0f && c_lo < 1e-36f;
         force[2 * p + 1] = c_hi > 0.0f && c_hi < 1e-36f;
     }
-    const uint32_t* tp = th + (ty * S) * Sh::SCOLS + tx + HC;
+    const uint32_t* tp = th + (ty * S) * Sh::SCOLS + tx + Sh::HCP;
     for (int dc = -HC; dc <= HC; ++dc) {
         if (dc >= -GC && dc <= GC) K3Rows<HL, GL, true, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
         else K3Rows<HL, GL, false, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
@@ -273,7 +354,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         const bool valid = i < ns;
         const int code = valid ? surv[i] : 0;                      // idle groups chew on tile cell (0, 0)
         const int tl = code >> 16, tcx = code & 0xffff;
-        const int cidx = (tl + HL) * Sh::SCOLS + tcx + HC;
+        const int cidx = (tl + HL) * Sh::SCOLS + tcx + Sh::HCP;
         const float cut = tf[cidx];
         float v[NQ];
         RDP_UNROLL
@@ -327,6 +408,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         const int line = r0 + rl, word = c0 / 32 + w;
         if (line < a.n_range && word < a.words_per_row) bm[(long long)line * a.words_per_row + word] = bits[i];
     }
+    __syncthreads();                                      // the tile's shared state is reused by the next tile
+    }   // tile loop
 }
 
 // ------------------------------------------------------------------------------------------

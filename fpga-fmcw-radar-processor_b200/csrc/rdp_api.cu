@@ -9,6 +9,9 @@
 #include "k2_doppler.cuh"
 #include "k3_cfar.cuh"
 
+#ifndef RDP_EMU
+#include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through the runtime
+#endif
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -41,10 +44,12 @@ struct K2Launcher {
 };
 struct K3Launcher {
     int trows, tcols;            // 0,0 => generic kernel
+    int srows, scols;            // shared-memory tile (+ halo) = TMA box
     size_t smem;
-    cudaError_t (*prepare)(size_t smem);
+    cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(long long grid, size_t smem, cudaStream_t st, const float* rd_map, float* cfar_out,
-                   uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c);
+                   uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
+                   const CUtensorMap* tmap);
 };
 
 template <class K>
@@ -147,26 +152,29 @@ bool k2_for(int n, K2Launcher* out) {
 template <int HL, int HC, int GL, int GC, int S, int TCOLS>
 struct K3Inst {
     using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
-    static cudaError_t prepare(size_t s) {
-        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>, 256, s, nullptr);
+    static cudaError_t prepare(size_t s, int* occ) {
+        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>, 256, s, occ);
     }
     static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out,
-                       uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c) {
+                       uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
+                       const CUtensorMap* tmap) {
         RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>), (unsigned)grid, 256, s, st, rd_map, cfar_out, det_bits,
-                   a, tiles_r, tiles_c);
+                   a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
     }
-    static K3Launcher get() { return K3Launcher{Sh::TROWS, TCOLS, Sh::smem_bytes(), &prepare, &launch}; }
+    static K3Launcher get() {
+        return K3Launcher{Sh::TROWS, TCOLS, Sh::SROWS, Sh::SCOLS, Sh::smem_bytes(), &prepare, &launch};
+    }
 };
 struct K3Generic {
-    static cudaError_t prepare(size_t) { return cudaSuccess; }
+    static cudaError_t prepare(size_t, int* occ) { if (occ) *occ = 1; return cudaSuccess; }
     static void launch(long long grid, size_t, cudaStream_t st, const float* rd_map, float* cfar_out,
-                       uint32_t* det_bits, CfarArgs a, int, int) {
+                       uint32_t* det_bits, CfarArgs a, int, int, long long, int, const CUtensorMap*) {
         long long n_words = grid;   // grid carries the bitmask word count for the generic kernel
         long long blocks = (n_words + 7) / 8;
         if (blocks > 148 * 64) blocks = 148 * 64;
         RDP_LAUNCH(k3_cfar_generic_kernel, (unsigned)blocks, 256, 0, st, rd_map, cfar_out, det_bits, a, n_words);
     }
-    static K3Launcher get() { return K3Launcher{0, 0, 0, &prepare, &launch}; }
+    static K3Launcher get() { return K3Launcher{0, 0, 0, 0, 0, &prepare, &launch}; }
 };
 
 K3Launcher k3_for(int hl, int hc, int gl, int gc) {
@@ -211,7 +219,9 @@ struct rdp_handle {
     K1Launcher k1;
     K2Launcher k2;
     K3Launcher k3;
-    int k1_grid_cap = 1, k2_grid_cap = 1;
+    int k1_grid_cap = 1, k2_grid_cap = 1, k3_grid_cap = 1;
+    void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved at create (NULL: manual tile loads)
+    int cfar_tma = 0;               // last CFAR launch staged its tiles with TMA
     int k1_tile_chirps = 1;
     size_t k1_smem = 0;
     CfarArgs cfar;
@@ -314,13 +324,38 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     const long long maps = (long long)n_cpi * c.n_channels;
     if (maps == 0) return RDP_OK;
     stage_begin(h, 2);
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
     if (h->k3.trows == 0) {
-        h->k3.launch(maps * c.n_samples * h->cfar.words_per_row, 0, h->stream, rd_map, cfar_out, h->det_bits, h->cfar, 0, 0);
+        h->k3.launch(maps * c.n_samples * h->cfar.words_per_row, 0, h->stream, rd_map, cfar_out, h->det_bits, h->cfar, 0, 0,
+                     0, 0, &tmap);
     } else {
         const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
         const int tiles_c = (c.n_chirps + h->k3.tcols - 1) / h->k3.tcols;
-        h->k3.launch(maps * tiles_r * tiles_c, h->k3.smem, h->stream, rd_map, cfar_out, h->det_bits, h->cfar,
-                     tiles_r, tiles_c);
+        const long long n_tiles = maps * tiles_r * tiles_c;
+        int use_tma = 0;
+#ifndef RDP_EMU
+        // TMA stages the (tile + halo) box and zero-fills outside the map == cfar_edges ZERO; the flat-raster
+        // edge rule wraps across range lines, which a tiled tensor map cannot express -> manual loads
+        if (h->encode_tiled && !h->cfar.raster && ((uintptr_t)rd_map & 15) == 0 && maps < (1ll << 31)) {
+            typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            const cuuint64_t gdim[3] = {(cuuint64_t)c.n_chirps, (cuuint64_t)c.n_samples, (cuuint64_t)maps};
+            const cuuint64_t gstr[2] = {(cuuint64_t)c.n_chirps * 4, (cuuint64_t)c.n_chirps * c.n_samples * 4};
+            const cuuint32_t box[3] = {(cuuint32_t)h->k3.scols, (cuuint32_t)h->k3.srows, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = reinterpret_cast<encode_fn>(h->encode_tiled)(
+                &tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(rd_map), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            use_tma = (r == CUDA_SUCCESS);
+        }
+#endif
+        h->cfar_tma = use_tma;
+        const long long grid = n_tiles < h->k3_grid_cap ? n_tiles : h->k3_grid_cap;
+        h->k3.launch(grid, h->k3.smem, h->stream, rd_map, cfar_out, h->det_bits, h->cfar, tiles_r, tiles_c, n_tiles, use_tma,
+                     &tmap);
     }
     stage_end(h);
     int rc = launch_check(h, "k3_cfar_kernel");
@@ -489,7 +524,18 @@ int init_handle(rdp_handle* h) {
     a.max_dets = c.max_dets_per_cpi;
     a.words_per_row = (c.n_chirps + 31) / 32;
     h->k3 = k3_for(a.half_l, a.half_c, a.guard_l, a.guard_c);
-    RDP_CUDA(h, h->k3.prepare(h->k3.smem));
+    RDP_CUDA(h, h->k3.prepare(h->k3.smem, &occ));
+    h->k3_grid_cap = h->sm_count * occ;
+#ifndef RDP_EMU
+    {
+        cudaDriverEntryPointQueryResult qres;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            h->encode_tiled = fn;
+        cudaGetLastError();
+    }
+#endif
 
     // chunking: keep the range-major intermediate of one chunk L2-resident between K1 and K2
     const size_t xrc_per_cpi = cells_per_cpi(c) * sizeof(float2);
@@ -620,6 +666,7 @@ int rdp_get_info(const rdp_handle* h, rdp_info* info) {
     info->chunk_cpis = h->chunk;
     info->scratch_bytes = h->scratch_bytes;
     info->kernel_launches = h->launches;
+    info->cfar_tma = h->cfar_tma;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess)
         std::snprintf(info->device_name, sizeof(info->device_name), "%s", prop.name);

@@ -49,7 +49,7 @@ class RdpConfig(C.Structure):
 
 class RdpInfo(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("sm_count", C.c_int32),
-                ("chunk_cpis", C.c_int32), ("scratch_bytes", C.c_int64), ("kernel_launches", C.c_int64),
+                ("chunk_cpis", C.c_int32), ("cfar_tma", C.c_int32), ("reserved", C.c_int32), ("scratch_bytes", C.c_int64), ("kernel_launches", C.c_int64),
                 ("device_name", C.c_char * 128)]
 
 
@@ -204,7 +204,7 @@ class RadarCore:
     def info(self) -> dict:
         i = RdpInfo()
         self._check(self.lib.rdp_get_info(self.h, C.byref(i)))
-        return dict(abi_version=i.abi_version, device=i.device, sm_count=i.sm_count, chunk_cpis=i.chunk_cpis,
+        return dict(abi_version=i.abi_version, device=i.device, sm_count=i.sm_count, chunk_cpis=i.chunk_cpis, cfar_tma=bool(i.cfar_tma),
                     scratch_bytes=i.scratch_bytes, kernel_launches=i.kernel_launches,
                     device_name=i.device_name.decode())
 

@@ -102,6 +102,8 @@ typedef struct rdp_info {
     int32_t device;
     int32_t sm_count;
     int32_t chunk_cpis;        /* resolved chunk size                                     */
+    int32_t cfar_tma;          /* 1 if the last CFAR launch staged its tiles with TMA     */
+    int32_t reserved;
     int64_t scratch_bytes;     /* device memory owned by the handle                       */
     int64_t kernel_launches;   /* kernels launched by this handle since creation          */
     char    device_name[128];
