@@ -169,6 +169,7 @@ def main():
 
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: ONE JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
