@@ -45,11 +45,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
+def ncu_traffic(kernel, cpis_per_launch):
+    """dram read+write bytes per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json holds bytes per CPI; a launch covers cpis_per_launch CPIs)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(kernel)
+            per_cpi = json.load(f).get(kernel)
+        return None if per_cpi is None else per_cpi * cpis_per_launch
     except Exception:
         return None
 
@@ -249,7 +251,9 @@ def main():
     dom = max(("range", "doppler", "cfar"), key=lambda k: stages.get(k, {}).get("ms_total_per_step", 0.0))
     kernel_names = {"range": "k1_range_kernel", "doppler": "k2_doppler_kernel", "cfar": "k3_cfar_kernel"}
     roofline = {"bound": "hbm", "kernel": kernel_names[dom], "achieved": stages[dom]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": ncu_traffic(kernel_names[dom]),
+                "unit": "GB/s", "frac": stages[dom]["frac"],
+                "traffic": ncu_traffic(kernel_names[dom], n_cpi / max(1, stages[dom]["launches_per_step"])),
+                "algorithmic_bytes_per_launch": stages[dom]["alg_bytes_per_cell"] * CELLS * n_cpi / max(1, stages[dom]["launches_per_step"]),
                 "peak_source": peak_src, "stages": stages,
                 "note": "K3 (OS-CFAR, 128 reference cells per cell) is ALU-bound, not HBM-bound; see DESIGN.md"}
 
