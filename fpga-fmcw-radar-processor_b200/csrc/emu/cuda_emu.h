@@ -190,6 +190,11 @@ static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch
 static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fmul_rz(float a, float b) {          // round toward zero (operands >= 0 here)
+    double p = (double)a * (double)b; float r = (float)p;
+    if ((double)r > p) r = std::nextafterf(r, 0.0f);
+    return r;
+}
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 
 // ---- runtime API subset ------------------------------------------------------------------

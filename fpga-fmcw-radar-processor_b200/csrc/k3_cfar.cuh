@@ -38,7 +38,15 @@ struct CfarArgs {
     int raster;                             // cfar_edges
     int max_dets;
     int words_per_row;                      // bitmask words per range line = ceil(n_doppler / 32)
+    int int_mode;                           // 1: the map holds unsigned integers and the decision is the bit-exact
+                                            //    integer arithmetic of os_cfar_2d.vhd (DATA_WIDTH = 17)
+    int is1, ismin, isnom, ismax;           // the scales as integers (int_mode)
 };
+
+// magnitude word -> float for the pre-filter; integers below 2^24 convert exactly
+__device__ __forceinline__ float cfar_as_float(float raw, int int_mode) {
+    return int_mode ? (float)(uint32_t)__float_as_int(raw) : raw;
+}
 
 // magnitude of flat cell (line, col) of one map under the edge rule
 __device__ __forceinline__ float cfar_fetch(const float* __restrict__ m, int line, int col,
@@ -205,7 +213,7 @@ struct K3Rows<HL, GL, GUARD_COL, NROWS, NROWS> {
                                                const uint32_t (&)[4], const uint32_t (&)[4], uint32_t (&)[4]) {}
 };
 
-template <int HL, int HC, int GL, int GC, int S, int TCOLS>
+template <int HL, int HC, int GL, int GC, int S, int TCOLS, bool INT_MODE>
 __global__ void __launch_bounds__(256)
 k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, uint32_t* __restrict__ det_bits,
                CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
@@ -273,7 +281,9 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         if (threadIdx.x == 0 && tile_id + gridDim.x < n_tiles) issue(tile_id + gridDim.x, stage ^ 1);
         mbar_wait(mbar + stage, (uint32_t)((iter >> 1) & 1));
         for (int i = threadIdx.x; i < Sh::SROWS * Sh::SCOLS; i += 256) {
-            const uint32_t lo = bf16_down(__fmul_rn(tf[i], a.s1));
+            // int_mode: round the product toward zero so that ref_lo never exceeds the exact integer product
+            const float fv = cfar_as_float(tf[i], INT_MODE);
+            const uint32_t lo = bf16_down(INT_MODE ? __fmul_rz(fv, a.s1) : __fmul_rn(fv, a.s1));
             th[i] = lo | (lo << 16);
         }
     } else
@@ -297,7 +307,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                         v = __ldg(m + row_base + c);
                     }
                     tf[lr * Sh::SCOLS + lc] = v;
-                    const uint32_t lo = bf16_down(__fmul_rn(v, a.s1));
+                    const float fv = cfar_as_float(v, INT_MODE);
+                    const uint32_t lo = bf16_down(INT_MODE ? __fmul_rz(fv, a.s1) : __fmul_rn(fv, a.s1));
                     th[lr * Sh::SCOLS + lc] = lo | (lo << 16);
                 }
             }
@@ -312,8 +323,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     bool force[S];
     RDP_UNROLL
     for (int p = 0; p < 4; ++p) {
-        const float c_lo = tf[(ty * S + 2 * p + HL) * Sh::SCOLS + tx + Sh::HCP];
-        const float c_hi = tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + Sh::HCP];
+        const float c_lo = cfar_as_float(tf[(ty * S + 2 * p + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
+        const float c_hi = cfar_as_float(tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
         const uint32_t h0 = bf16_up(c_lo), h1 = bf16_up(c_hi);
         cb[p] = h0 | (h1 << 16);
         cl[p] = h0;
@@ -355,6 +366,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         const int code = valid ? surv[i] : 0;                      // idle groups chew on tile cell (0, 0)
         const int tl = code >> 16, tcx = code & 0xffff;
         const int cidx = (tl + HL) * Sh::SCOLS + tcx + Sh::HCP;
+        bool det;
+        if (!INT_MODE) {
         const float cut = tf[cidx];
         float v[NQ];
         RDP_UNROLL
@@ -393,7 +406,50 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         RDP_UNROLL
         for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         const int n_lt = c - NZ;                                   // zero slots: 0 - cut < 0 (cut > 0 here)
-        const bool det = valid && cut > 0.0f && n_lt >= a.rank_idx + 1;   // cut > x_k * scale  (:213)
+        det = valid && cut > 0.0f && n_lt >= a.rank_idx + 1;       // cut > x_k * scale  (:213)
+        } else {
+        // bit-exact integer arithmetic of os_cfar_2d.vhd (17-bit magnitudes; values < 2^24 supported)
+        const uint32_t* ti = reinterpret_cast<const uint32_t*>(tf);
+        const int cut = (int)ti[cidx];
+        int v[NQ];
+        RDP_UNROLL
+        for (int q = 0; q < NQ; ++q) {
+            const int2 w = *reinterpret_cast<const int2*>(wtab + 2 * (q * G + sub));
+            v[q] = (int)ti[cidx * w.x + w.y];
+        }
+        int scale = a.is1;
+        if (a.adaptive) {
+            unsigned long long s = 0ull;                          // sum_refs (:163), 25 bits in the RTL
+            RDP_UNROLL
+            for (int q = 0; q < NQ; ++q) s += (unsigned long long)(uint32_t)v[q];
+            RDP_UNROLL
+            for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            // mean_val = resize(sum_refs / N_REF, 17) (:189): floor division (exact through float64: the quotient
+            // of integers below 2^53 is either an integer or at least 1/N_REF away from one), truncated to 17 bits
+            const int mean = (int)((unsigned long long)((double)s / (double)a.n_ref) & 0x1ffffull);
+            const int lo = mean >> 1;                             // shift_right(mean_val, 1)
+            const int hi = (mean + lo) & 0x1ffff;                 // 17-bit unsigned add (:193)
+            uint32_t c_gt_hi = 0u, c_lt_lo = 0u;
+            RDP_UNROLL
+            for (int q = 0; q < NQ; ++q) {
+                c_gt_hi += (uint32_t)(hi - v[q]) >> 31;           // v > hi
+                c_lt_lo += (uint32_t)(v[q] - lo) >> 31;           // v < lo (zero slots count iff lo > 0)
+            }
+            int packed = (int)(c_gt_hi | (c_lt_lo << 16));
+            RDP_UNROLL
+            for (int o = G / 2; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
+            const int n_le_hi = a.n_ref - (packed & 0xffff);
+            const int n_lt_lo = (packed >> 16) - (lo > 0 ? NZ : 0);
+            scale = (n_le_hi <= a.rank_idx) ? a.ismax : (n_lt_lo >= a.rank_idx + 1) ? a.ismin : a.isnom;   // :191-199
+        }
+        int c = 0;
+        RDP_UNROLL
+        for (int q = 0; q < NQ; ++q) c += (int)((uint32_t)(v[q] * scale - cut) >> 31);     // ref * scale < cut (:204,213)
+        RDP_UNROLL
+        for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        det = valid && cut > 0 && (c - NZ) >= a.rank_idx + 1;
+        }
+        const float cut = tf[cidx];                                // raw word: written back unchanged in either mode
         if (det && sub == 0) {
             atomicOr(bits + tl * Sh::TWORDS + (tcx >> 5), 1u << (tcx & 31));
             if (cfar_out)
@@ -520,7 +576,7 @@ k4_emit_kernel(const uint32_t* __restrict__ det_bits, const int* __restrict__ ro
                 d.channel = line_all / a.n_range;
                 d.range = line_all % a.n_range;
                 d.doppler = col;
-                d.mag = __ldg(rd_map + row * a.n_doppler + col);
+                d.mag = cfar_as_float(__ldg(rd_map + row * a.n_doppler + col), a.int_mode);
                 out[slot] = d;
             }
             ++slot;

@@ -153,13 +153,19 @@ template <int HL, int HC, int GL, int GC, int S, int TCOLS>
 struct K3Inst {
     using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
     static cudaError_t prepare(size_t s, int* occ) {
-        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>, 256, s, occ);
+        cudaError_t e = prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS, true>, 256, s, nullptr);
+        if (e != cudaSuccess) return e;
+        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS, false>, 256, s, occ);
     }
     static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out,
                        uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
                        const CUtensorMap* tmap) {
-        RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS>), (unsigned)grid, 256, s, st, rd_map, cfar_out, det_bits,
-                   a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
+        if (a.int_mode)
+            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS, true>), (unsigned)grid, 256, s, st, rd_map, cfar_out,
+                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
+        else
+            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS, false>), (unsigned)grid, 256, s, st, rd_map, cfar_out,
+                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
     }
     static K3Launcher get() {
         return K3Launcher{Sh::TROWS, TCOLS, Sh::SROWS, Sh::SCOLS, Sh::smem_bytes(), &prepare, &launch};
@@ -319,15 +325,17 @@ int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map) {
 // K3 + K4 on n_cpi <= chunk maps-worth of CPIs: bitmask, then ordered compaction into dets / counts / status
 // (all three already offset to this chunk); cpi_label is the CPI index written into the records.
 int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp_det* dets, int* counts,
-             uint32_t* status, int cpi_label) {
+             uint32_t* status, int cpi_label, int int_mode = 0) {
     const rdp_config& c = h->cfg;
+    CfarArgs args = h->cfar;
+    args.int_mode = int_mode;
     const long long maps = (long long)n_cpi * c.n_channels;
     if (maps == 0) return RDP_OK;
     stage_begin(h, 2);
     CUtensorMap tmap;
     std::memset(&tmap, 0, sizeof(tmap));
     if (h->k3.trows == 0) {
-        h->k3.launch(maps * c.n_samples * h->cfar.words_per_row, 0, h->stream, rd_map, cfar_out, h->det_bits, h->cfar, 0, 0,
+        h->k3.launch(maps * c.n_samples * args.words_per_row, 0, h->stream, rd_map, cfar_out, h->det_bits, args, 0, 0,
                      0, 0, &tmap);
     } else {
         const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
@@ -337,7 +345,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
 #ifndef RDP_EMU
         // TMA stages the (tile + halo) box and zero-fills outside the map == cfar_edges ZERO; the flat-raster
         // edge rule wraps across range lines, which a tiled tensor map cannot express -> manual loads
-        if (h->encode_tiled && !h->cfar.raster && ((uintptr_t)rd_map & 15) == 0 && maps < (1ll << 31)) {
+        if (h->encode_tiled && !args.raster && ((uintptr_t)rd_map & 15) == 0 && maps < (1ll << 31)) {
             typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -354,7 +362,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
 #endif
         h->cfar_tma = use_tma;
         const long long grid = n_tiles < h->k3_grid_cap ? n_tiles : h->k3_grid_cap;
-        h->k3.launch(grid, h->k3.smem, h->stream, rd_map, cfar_out, h->det_bits, h->cfar, tiles_r, tiles_c, n_tiles, use_tma,
+        h->k3.launch(grid, h->k3.smem, h->stream, rd_map, cfar_out, h->det_bits, args, tiles_r, tiles_c, n_tiles, use_tma,
                      &tmap);
     }
     stage_end(h);
@@ -364,7 +372,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, 256, 0, h->stream, h->det_bits, h->row_off, counts, status, h->cfar);
     const long long total_rows = maps * c.n_samples;
     RDP_LAUNCH(k4_emit_kernel, (unsigned)((total_rows + 7) / 8), 256, 0, h->stream, h->det_bits, h->row_off, rd_map, dets,
-               h->cfar, total_rows, cpi_label);
+               args, total_rows, cpi_label);
     h->launches += 1;
     stage_end(h);
     return launch_check(h, "k4 compaction kernels");
@@ -521,6 +529,8 @@ int init_handle(rdp_handle* h) {
         a.s1 = (float)c.scale_override;
     }
     a.raster = c.cfar_edges == RDP_EDGES_RASTER;
+    a.int_mode = 0;
+    a.is1 = (int)a.s1; a.ismin = c.scale_min; a.isnom = c.scale_nom; a.ismax = c.scale_max;
     a.max_dets = c.max_dets_per_cpi;
     a.words_per_row = (c.n_chirps + 31) / 32;
     h->k3 = k3_for(a.half_l, a.half_c, a.guard_l, a.guard_c);
@@ -703,6 +713,26 @@ int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfa
         const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
         int rc = run_cfar(h, rd_map + (size_t)base * cells, n, cfar_out ? cfar_out + (size_t)base * cells : nullptr,
                           dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base);
+        if (rc) return rc;
+    }
+    return RDP_OK;
+}
+
+int rdp_cfar_stage_u32(rdp_handle* h, const uint32_t* mag_map, int32_t n_cpi, uint32_t* cfar_out, rdp_det* dets,
+                       int32_t* n_dets, uint32_t* status) {
+    if (!h || !mag_map || !dets || !n_dets || !status || n_cpi < 0)
+        return fail(h, RDP_E_INVALID, "rdp_cfar_stage_u32: bad argument");
+    if (h->k3.trows == 0)
+        return fail(h, RDP_E_INVALID, "rdp_cfar_stage_u32: no tiled kernel instance for this CFAR window shape");
+    const rdp_config& c = h->cfg;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    const size_t cells = cells_per_cpi(c);
+    for (int base = 0; base < n_cpi; base += h->chunk) {
+        const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
+        // the kernels move 32-bit words; in integer mode they are read as unsigned integers
+        int rc = run_cfar(h, reinterpret_cast<const float*>(mag_map) + (size_t)base * cells, n,
+                          cfar_out ? reinterpret_cast<float*>(cfar_out) + (size_t)base * cells : nullptr,
+                          dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base, 1);
         if (rc) return rc;
     }
     return RDP_OK;

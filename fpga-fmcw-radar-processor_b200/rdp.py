@@ -67,6 +67,7 @@ SYMBOLS = {
     "rdp_range_stage": (C.c_int, [_VP, _VP, _I32, _VP]),
     "rdp_doppler_stage": (C.c_int, [_VP, _VP, _I32, _VP]),
     "rdp_cfar_stage": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "rdp_cfar_stage_u32": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "rdp_device_alloc": (C.c_int, [_VP, _SZ, C.POINTER(_VP)]),
     "rdp_device_free": (C.c_int, [_VP, _VP]),
     "rdp_host_alloc": (C.c_int, [_VP, _SZ, C.POINTER(_VP)]),
@@ -340,6 +341,29 @@ class RadarCore:
             dets, counts = self.unpack_device_dets(d_dets, d_counts, n_cpi)
             status = d_status.download((n_cpi,), np.uint32)
             dense = d_dense.download(rd_map.shape, np.float32) if want_dense else None
+            return dets, counts, status, dense
+        finally:
+            for b in (d_map, d_dense, d_dets, d_counts, d_status):
+                if b is not None:
+                    b.free()
+
+    def cfar_stage_fixed(self, mag_map: np.ndarray, want_dense: bool = True):
+        """Fixed-point CFAR stage (rdp_cfar_stage_u32): unsigned integer magnitudes in, decisions by the
+        bit-exact integer arithmetic of rtl/src/os_cfar_2d.vhd.  -> (detections, n_dets, status, cfar_out uint32)."""
+        mag_map = np.ascontiguousarray(mag_map, dtype=np.uint32).reshape(-1, self.n_channels, self.n_range, self.n_doppler)
+        n_cpi = mag_map.shape[0]
+        d_map = self.device_buffer(mag_map.nbytes).upload(mag_map)
+        d_dense = self.device_buffer(mag_map.nbytes) if want_dense else None
+        d_dets = self.device_buffer(n_cpi * self.max_dets_per_cpi * DET_DTYPE.itemsize)
+        d_counts = self.device_buffer(n_cpi * 4)
+        d_status = self.device_buffer(n_cpi * 4)
+        try:
+            self._check(self.lib.rdp_cfar_stage_u32(self.h, d_map.ptr, n_cpi, d_dense.ptr if want_dense else None,
+                                                    d_dets.ptr, d_counts.ptr, d_status.ptr))
+            self.sync()
+            dets, counts = self.unpack_device_dets(d_dets, d_counts, n_cpi)
+            status = d_status.download((n_cpi,), np.uint32)
+            dense = d_dense.download(mag_map.shape, np.uint32) if want_dense else None
             return dets, counts, status, dense
         finally:
             for b in (d_map, d_dense, d_dets, d_counts, d_status):

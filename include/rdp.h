@@ -155,6 +155,16 @@ int rdp_doppler_stage(rdp_handle* h, const void* x_rc, int32_t n_cpi, float* rd_
 int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfar_out,
                    rdp_det* dets, int32_t* n_dets, uint32_t* status);
 
+/* Fixed-point CFAR stage: the map holds UNSIGNED INTEGER magnitudes (the 17-bit words of
+ * magnitude_calc; values below 2^24 are supported) and every decision is the bit-exact integer
+ * arithmetic of rtl/src/os_cfar_2d.vhd:152-217 -- integer sum, mean = floor(sum / N_REF)
+ * truncated to 17 bits, lo = mean >> 1, hi = (mean + lo) mod 2^17, exact product x_k * scale.
+ * cfar_out (nullable) is the RTL's output word per cell: the CUT magnitude or 0.  Records carry
+ * the magnitude converted to float.  Needs a tiled kernel instance for the window shape
+ * (the radar_core, tb_os_cfar_2d, legacy and "wide" shapes have one).                        */
+int rdp_cfar_stage_u32(rdp_handle* h, const uint32_t* mag_map, int32_t n_cpi, uint32_t* cfar_out,
+                       rdp_det* dets, int32_t* n_dets, uint32_t* status);
+
 /* Device / pinned-host memory owned by the caller (so a ctypes host needs no other CUDA binding). */
 int rdp_device_alloc(rdp_handle* h, size_t bytes, void** ptr);
 int rdp_device_free(rdp_handle* h, void* ptr);

@@ -178,3 +178,46 @@ def case_golden_chirp(make_core, golden_chirp_1024, n_chirps=16):
     assert (int(r), int(d)) == (290, 3)
     assert float(np.abs(rd_map[0] - ref_map).max()) <= MAP_TOL * float(ref_map.max())
     assert (0, 0, 290, 3) in det_cells(dets)
+
+
+def case_cfar_fixed_point(make_core, n_range=64, n_doppler=64, seed=3, **kw):
+    """Fixed-point CFAR stage (rdp_cfar_stage_u32) against the bit-exact integer restatement of
+    rtl/src/os_cfar_2d.vhd (oracle.rtl_fixed.os_cfar_2d): adaptive scale, floor division, 17-bit
+    wrap and all -- the dense RTL output word and the detection list must be identical."""
+    rng = np.random.default_rng(seed)
+    m = rng.integers(20, 600, size=(2, n_range, n_doppler)).astype(np.uint32)
+    m[0, n_range // 2, n_doppler // 2] = 45056                   # largest 17-bit magnitude (magnitude_calc.vhd:78-81)
+    m[0, n_range // 2, n_doppler // 2 + 1] = 20000
+    m[1, 3, 5] = 9000
+    m[1, :, 7] += 2500                                           # a ridge: windows whose mean is dominated by a few cells
+    m[0, 0, 0] = 7000
+    m[0, n_range - 1, n_doppler - 1] = 7000
+    kw.setdefault("max_dets_per_cpi", 1 << 16)
+    with make_core(n_range=n_range, n_doppler=n_doppler, n_channels=2, **kw) as c:
+        dets, counts, status, dense = c.cfar_stage_fixed(m[None])
+    names = dict(cfar_ref_r="ref_range", cfar_ref_d="ref_doppler", cfar_guard_r="guard_range", cfar_guard_d="guard_doppler",
+                 rank_pct="rank_pct", scale_min="scale_min", scale_nom="scale_nom", scale_max="scale_max",
+                 scale_override="scale_override", cfar_edges="edges", cfar_axes="axes")
+    okw = {names[k]: v for k, v in kw.items() if k in names}
+    exp = np.stack([fx.os_cfar_2d(m[i], **okw) for i in range(2)])
+    assert np.array_equal(dense[0], exp)
+    n_exp = int(np.count_nonzero(exp))
+    assert counts.tolist() == [n_exp] and n_exp > 0 and status.tolist() == [0]
+    ref = np.concatenate([fx.detections_from_cfar(exp[i]) for i in range(2)])
+    assert np.array_equal(dets["range"], ref[:, 0]) and np.array_equal(dets["doppler"], ref[:, 1])
+    assert np.array_equal(dets["mag"].astype(np.int64), ref[:, 2])
+    check_canonical(dets)
+
+
+def case_cfar_fixed_tb_map(make_core):
+    """rtl/src/tb_os_cfar_2d.vhd:42-75 map, (3,2,1,1), adaptive scale: bit-exact against the integer oracle,
+    both targets detected (T1, :123-134)."""
+    m = st.cfar_tb_map()
+    for edges in ("zero", "raster"):
+        with make_core(n_range=64, n_doppler=32, cfar_ref_r=3, cfar_ref_d=2, cfar_guard_r=1, cfar_guard_d=1,
+                       cfar_edges=edges) as c:
+            dets, counts, status, dense = c.cfar_stage_fixed(m[None, None])
+        exp = fx.os_cfar_2d(m, 3, 2, 1, 1, edges=edges)
+        assert np.array_equal(dense[0, 0], exp)
+        cells = {(int(r), int(d)) for r, d in zip(dets["range"], dets["doppler"])}
+        assert (30, 16) in cells and (50, 8) in cells and counts[0] >= 2

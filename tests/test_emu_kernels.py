@@ -71,3 +71,13 @@ def test_overflow_flag(make_core):
 
 def test_chunking_invariance(make_core):
     pc.case_chunking_invariance(make_core)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(cfar_edges="raster"), dict(scale_override=3), dict(cfar_axes="as_named"),
+                                dict(rank_pct=50, scale_min=1, scale_nom=3, scale_max=5)])
+def test_cfar_fixed_point_bit_exact(make_core, kw):
+    pc.case_cfar_fixed_point(make_core, 32, 64, **kw)
+
+
+def test_cfar_fixed_tb_map(make_core):
+    pc.case_cfar_fixed_tb_map(make_core)

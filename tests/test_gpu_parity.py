@@ -91,6 +91,28 @@ def test_cfar_empty_and_flat_maps(make_core):
             assert counts.tolist() == [int(np.count_nonzero(ref))]
 
 
+# ---- fixed-point CFAR stage: bit-exact against the integer restatement of os_cfar_2d.vhd ---------------
+@pytest.mark.parametrize("nr,nd,kw", [
+    (512, 256, dict()), (1024, 128, dict(cfar_edges="raster")), (128, 64, dict(cfar_axes="as_named")),
+    (64, 64, dict(scale_override=2)), (64, 64, dict(scale_override=7)),
+    (64, 32, dict(cfar_ref_r=3, cfar_ref_d=2, cfar_guard_r=1, cfar_guard_d=1)),
+    (128, 128, dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2, cfar_edges="raster")),
+    (64, 64, dict(rank_pct=50, scale_min=1, scale_nom=3, scale_max=5)), (16, 8, dict()),
+])
+def test_cfar_fixed_point_bit_exact(make_core, nr, nd, kw):
+    pc.case_cfar_fixed_point(make_core, nr, nd, **kw)
+
+
+def test_cfar_fixed_tb_map(make_core):
+    pc.case_cfar_fixed_tb_map(make_core)
+
+
+def test_cfar_fixed_rejects_untiled_window(make_core):
+    with make_core(n_range=64, n_doppler=64, cfar_ref_r=1, cfar_ref_d=2, cfar_guard_r=0, cfar_guard_d=1) as c:
+        with pytest.raises(rdp.RdpError):
+            c.cfar_stage_fixed(np.ones((1, 1, 64, 64), np.uint32))
+
+
 # ---- whole path ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_cpi,n_ch,nc,ns,fmt,kw", [
     (2, 3, 256, 512, "int16", dict()),                                   # BASELINE config 3 shape
