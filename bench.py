@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--max-dets", type=int, default=32768, help="detection-list capacity per CPI")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stream", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -278,6 +279,39 @@ def main():
                "d2h_bytes_per_step": int(d2h), "cpis_per_step": ne, "steps": reps,
                "api": "RadarCore.process (rdp_process_host), pinned host buffers"}
 
+    # ---- streaming ingest (BASELINE config 5): one CPI (12 channels) per submission from pinned host memory
+    streaming = None
+    if not args.no_e2e and not args.no_stream:
+        def stream_run(n_slots, n_sub):
+            core.stream_open(n_slots, 1)
+            bufs = []
+            for k in range(n_slots):
+                b = core.pinned_empty((1,) + uniq.shape[1:], uniq.dtype)
+                b[0] = uniq[k % uniq.shape[0]]
+                bufs.append(b)
+            t_sub = [0.0] * n_slots
+            lat = []
+            t_start = time.perf_counter()
+            for i in range(n_sub + n_slots):
+                slot = i % n_slots
+                if i >= n_slots:
+                    core.stream_wait(slot)
+                    lat.append(time.perf_counter() - t_sub[slot])
+                if i < n_sub:
+                    t_sub[slot] = time.perf_counter()
+                    core.stream_submit(slot, bufs[slot])
+            dt = time.perf_counter() - t_start
+            core.stream_close()
+            lat = np.sort(np.asarray(lat[n_slots:])) * 1e3           # drop the pipeline fill
+            return {"slots": n_slots, "submissions": n_sub, "cpis_per_s": n_sub / dt,
+                    "latency_ms_p50": float(lat[len(lat) // 2]), "latency_ms_p99": float(lat[int(len(lat) * 0.99)])}
+        stream_run(2, 50)                                            # warm-up
+        barrier_max(0.0)
+        one = stream_run(1, 300)
+        three = stream_run(3, 1500)
+        streaming = {"unit": UNIT, "value": world * three["cpis_per_s"], "pipelined": three, "one_in_flight": one,
+                     "h2d_bytes_per_submission": int(per_cpi), "api": "rdp_stream_submit / rdp_stream_wait, pinned host ring"}
+
     # ---- CPU baseline on this box's host cores (bounded sample, rank 0, N = 1 only) ----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -298,7 +332,7 @@ def main():
                            "cfar": "ref 4/4 guard 2/1 rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
                            "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),
                            "device": info["device_name"], "cfar_tile_staging": "TMA" if core.info()["cfar_tma"] else "manual", "sharding": "CPIs dealt to ranks, no data-path collective"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "clocks": clocks, "e2e": e2e, "streaming": streaming, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu,
                 "detections_per_cpi_mean": float(counts.mean()), "status_or": int(np.bitwise_or.reduce(status))}
         print(json.dumps(line), flush=True)

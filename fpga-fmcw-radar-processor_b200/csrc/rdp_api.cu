@@ -199,6 +199,22 @@ K3Launcher k3_for(int hl, int hc, int gl, int gc) {
 
 }  // namespace
 
+// One in-flight submission of the streaming ingest path (BASELINE config 5)
+struct StreamSlot {
+    cudaStream_t copy = nullptr;            // H2D of the cube and D2H of the results
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+    void* d_in = nullptr;
+    rdp_det* d_dets = nullptr;
+    rdp_det* d_packed = nullptr;
+    int* d_counts = nullptr;
+    uint32_t* d_status = nullptr;
+    rdp_det* h_packed = nullptr;            // page-locked results
+    int* h_counts = nullptr;
+    uint32_t* h_status = nullptr;
+    int n_cpi = 0;
+    bool busy = false;
+};
+
 struct rdp_handle {
     rdp_config cfg;
     int device = 0;
@@ -231,6 +247,8 @@ struct rdp_handle {
     int k1_tile_chirps = 1;
     size_t k1_smem = 0;
     CfarArgs cfar;
+    std::vector<StreamSlot> slots;
+    int slot_cpis = 0;
     bool stage_timing = false;
     std::vector<StageEvent> stage_events;
     float stage_ms[4] = {0, 0, 0, 0};
@@ -434,6 +452,17 @@ void release(rdp_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (auto& se : h->stage_events) { cudaEventDestroy(se.a); cudaEventDestroy(se.b); }
+    for (auto& sl : h->slots) {
+        void* dev[] = {sl.d_in, sl.d_dets, sl.d_packed, sl.d_counts, sl.d_status};
+        for (void* p : dev) if (p) cudaFree(p);
+        void* hst[] = {sl.h_packed, sl.h_counts, sl.h_status};
+        for (void* p : hst) if (p) cudaFreeHost(p);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.ev_out) cudaEventDestroy(sl.ev_out);
+        if (sl.copy) cudaStreamDestroy(sl.copy);
+    }
+    h->slots.clear();
     for (auto e : h->ev_copied) cudaEventDestroy(e);
     for (auto e : h->ev_done) cudaEventDestroy(e);
     for (auto e : h->ev_mapout) cudaEventDestroy(e);
@@ -812,6 +841,107 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
         RDP_CUDA(h, cudaMemcpyAsync(dets, h->packed, sizeof(rdp_det) * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
     RDP_CUDA(h, cudaStreamSynchronize(h->stream));
     if (rd_map) RDP_CUDA(h, cudaStreamSynchronize(h->d2h_stream));
+    return RDP_OK;
+}
+
+int rdp_stream_open(rdp_handle* h, int32_t n_slots, int32_t slot_cpis) {
+    if (!h || n_slots < 1 || n_slots > 16 || slot_cpis < 1) return fail(h, RDP_E_INVALID, "rdp_stream_open: bad argument");
+    if (!h->slots.empty()) return fail(h, RDP_E_INVALID, "rdp_stream_open: stream already open");
+    if (slot_cpis > h->chunk) return fail(h, RDP_E_CAPACITY, "slot_cpis %d exceeds the chunk size %d", slot_cpis, h->chunk);
+    const rdp_config& c = h->cfg;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    h->slot_cpis = slot_cpis;
+    h->slots.resize(n_slots);
+    const size_t in_bytes = (size_t)slot_cpis * cells_per_cpi(c) * in_bytes_per_sample(c);
+    const size_t n_rec = (size_t)slot_cpis * c.max_dets_per_cpi;
+    for (auto& sl : h->slots) {
+        RDP_CUDA(h, cudaStreamCreateWithFlags(&sl.copy, cudaStreamNonBlocking));
+        RDP_CUDA(h, cudaEventCreateWithFlags(&sl.ev_in, cudaEventDefault));
+        RDP_CUDA(h, cudaEventCreateWithFlags(&sl.ev_done, cudaEventDefault));
+        RDP_CUDA(h, cudaEventCreateWithFlags(&sl.ev_out, cudaEventDefault));
+        unsigned char* p = nullptr;
+        int rc = dev_alloc(h, &p, in_bytes); if (rc) return rc;
+        sl.d_in = p;
+        rc = dev_alloc(h, &sl.d_dets, n_rec); if (rc) return rc;
+        rc = dev_alloc(h, &sl.d_packed, n_rec); if (rc) return rc;
+        rc = dev_alloc(h, &sl.d_counts, (size_t)slot_cpis); if (rc) return rc;
+        rc = dev_alloc(h, &sl.d_status, (size_t)slot_cpis); if (rc) return rc;
+        RDP_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.h_packed), n_rec * sizeof(rdp_det), cudaHostAllocDefault));
+        RDP_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.h_counts), (size_t)slot_cpis * sizeof(int), cudaHostAllocDefault));
+        RDP_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.h_status), (size_t)slot_cpis * sizeof(uint32_t), cudaHostAllocDefault));
+    }
+    return RDP_OK;
+}
+
+int rdp_stream_submit(rdp_handle* h, int32_t slot, const void* cube, int32_t n_cpi) {
+    if (!h || !cube || slot < 0 || slot >= (int)h->slots.size() || n_cpi < 1 || n_cpi > h->slot_cpis)
+        return fail(h, RDP_E_INVALID, "rdp_stream_submit: bad argument");
+    StreamSlot& sl = h->slots[slot];
+    if (sl.busy) return fail(h, RDP_E_INVALID, "rdp_stream_submit: slot %d still in flight (call rdp_stream_wait)", slot);
+    const rdp_config& c = h->cfg;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    const size_t in_bytes = (size_t)n_cpi * cells_per_cpi(c) * in_bytes_per_sample(c);
+    // ingest on the slot's copy stream; the kernels of all slots share the compute stream (and its scratch), so
+    // the copy of submission i+1 overlaps the kernels of submission i
+    RDP_CUDA(h, cudaMemcpyAsync(sl.d_in, cube, in_bytes, cudaMemcpyHostToDevice, sl.copy));
+    RDP_CUDA(h, cudaEventRecord(sl.ev_in, sl.copy));
+    RDP_CUDA(h, cudaStreamWaitEvent(h->stream, sl.ev_in, 0));
+    int rc = run_range(h, sl.d_in, n_cpi, h->x_rc);
+    if (rc) return rc;
+    rc = run_doppler(h, h->x_rc, n_cpi, h->map_scratch[0]);
+    if (rc) return rc;
+    rc = run_cfar(h, h->map_scratch[0], n_cpi, nullptr, sl.d_dets, sl.d_counts, sl.d_status, 0);
+    if (rc) return rc;
+    h->launches += 1;
+    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, sl.d_dets, sl.d_counts, sl.d_packed, c.max_dets_per_cpi, 0);
+    rc = launch_check(h, "k5_pack_dets_kernel");
+    if (rc) return rc;
+    RDP_CUDA(h, cudaEventRecord(sl.ev_done, h->stream));
+    RDP_CUDA(h, cudaStreamWaitEvent(sl.copy, sl.ev_done, 0));
+    RDP_CUDA(h, cudaMemcpyAsync(sl.h_counts, sl.d_counts, sizeof(int) * (size_t)n_cpi, cudaMemcpyDeviceToHost, sl.copy));
+    RDP_CUDA(h, cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(uint32_t) * (size_t)n_cpi, cudaMemcpyDeviceToHost, sl.copy));
+    // the packed list is copied at full capacity so that one synchronisation suffices (slot_cpis is small)
+    RDP_CUDA(h, cudaMemcpyAsync(sl.h_packed, sl.d_packed, sizeof(rdp_det) * (size_t)n_cpi * c.max_dets_per_cpi,
+                                cudaMemcpyDeviceToHost, sl.copy));
+    RDP_CUDA(h, cudaEventRecord(sl.ev_out, sl.copy));
+    sl.n_cpi = n_cpi;
+    sl.busy = true;
+    return RDP_OK;
+}
+
+int rdp_stream_wait(rdp_handle* h, int32_t slot, const rdp_det** dets, const int32_t** n_dets, const uint32_t** status,
+                    int32_t* total) {
+    if (!h || slot < 0 || slot >= (int)h->slots.size()) return fail(h, RDP_E_INVALID, "rdp_stream_wait: bad argument");
+    StreamSlot& sl = h->slots[slot];
+    if (!sl.busy) return fail(h, RDP_E_INVALID, "rdp_stream_wait: slot %d has no submission in flight", slot);
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaEventSynchronize(sl.ev_out));
+    sl.busy = false;
+    long long t = 0;
+    for (int i = 0; i < sl.n_cpi; ++i)
+        t += sl.h_counts[i] < h->cfg.max_dets_per_cpi ? sl.h_counts[i] : h->cfg.max_dets_per_cpi;
+    if (dets) *dets = sl.h_packed;
+    if (n_dets) *n_dets = sl.h_counts;
+    if (status) *status = sl.h_status;
+    if (total) *total = (int32_t)t;
+    return RDP_OK;
+}
+
+int rdp_stream_close(rdp_handle* h) {
+    if (!h) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaDeviceSynchronize());
+    for (auto& sl : h->slots) {
+        void* dev[] = {sl.d_in, sl.d_dets, sl.d_packed, sl.d_counts, sl.d_status};
+        for (void* p : dev) if (p) cudaFree(p);
+        void* hst[] = {sl.h_packed, sl.h_counts, sl.h_status};
+        for (void* p : hst) if (p) cudaFreeHost(p);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.ev_out) cudaEventDestroy(sl.ev_out);
+        if (sl.copy) cudaStreamDestroy(sl.copy);
+    }
+    h->slots.clear();
     return RDP_OK;
 }
 

@@ -68,6 +68,10 @@ SYMBOLS = {
     "rdp_doppler_stage": (C.c_int, [_VP, _VP, _I32, _VP]),
     "rdp_cfar_stage": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "rdp_cfar_stage_u32": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "rdp_stream_open": (C.c_int, [_VP, _I32, _I32]),
+    "rdp_stream_submit": (C.c_int, [_VP, _I32, _VP, _I32]),
+    "rdp_stream_wait": (C.c_int, [_VP, _I32, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_I32)]),
+    "rdp_stream_close": (C.c_int, [_VP]),
     "rdp_device_alloc": (C.c_int, [_VP, _SZ, C.POINTER(_VP)]),
     "rdp_device_free": (C.c_int, [_VP, _VP]),
     "rdp_host_alloc": (C.c_int, [_VP, _SZ, C.POINTER(_VP)]),
@@ -346,6 +350,31 @@ class RadarCore:
             for b in (d_map, d_dense, d_dets, d_counts, d_status):
                 if b is not None:
                     b.free()
+
+    # -- streaming ingest (BASELINE config 5) -------------------------------------------------
+    def stream_open(self, n_slots: int = 3, slot_cpis: int = 1):
+        self._check(self.lib.rdp_stream_open(self.h, n_slots, slot_cpis))
+        self._slot_cpis = slot_cpis
+
+    def stream_submit(self, slot: int, cube: np.ndarray):
+        """Asynchronous: `cube` (ideally from pinned_empty) must stay untouched until stream_wait(slot)."""
+        cube = self._as_cube(cube)
+        self._check(self.lib.rdp_stream_submit(self.h, slot, _ptr(cube), cube.shape[0]))
+        return cube
+
+    def stream_wait(self, slot: int):
+        """-> (detections, n_dets, status) views of the slot's page-locked result buffers."""
+        pd, pn, ps, tot = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int32()
+        self._check(self.lib.rdp_stream_wait(self.h, slot, C.byref(pd), C.byref(pn), C.byref(ps), C.byref(tot)))
+        n = self._slot_cpis
+        counts = np.frombuffer((C.c_int32 * n).from_address(pn.value), dtype=np.int32)
+        status = np.frombuffer((C.c_uint32 * n).from_address(ps.value), dtype=np.uint32)
+        total = int(tot.value)
+        dets = np.frombuffer((C.c_ubyte * (max(total, 1) * DET_DTYPE.itemsize)).from_address(pd.value), dtype=DET_DTYPE)[:total]
+        return dets, counts, status
+
+    def stream_close(self):
+        self._check(self.lib.rdp_stream_close(self.h))
 
     def cfar_stage_fixed(self, mag_map: np.ndarray, want_dense: bool = True):
         """Fixed-point CFAR stage (rdp_cfar_stage_u32): unsigned integer magnitudes in, decisions by the

@@ -165,6 +165,21 @@ int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfa
 int rdp_cfar_stage_u32(rdp_handle* h, const uint32_t* mag_map, int32_t n_cpi, uint32_t* cfar_out,
                        rdp_det* dets, int32_t* n_dets, uint32_t* status);
 
+/* Streaming ingest (BASELINE config 5: pinned-host, multi-buffered chirp ingest).  n_slots
+ * submissions may be in flight; each carries up to slot_cpis CPIs (<= the handle's chunk size).
+ * rdp_stream_submit() is asynchronous: the host->device copy of submission i+1 overlaps the
+ * kernels of submission i (the reference streams one word per clock with no host at all:
+ * radar_core.vhd:25-29).  rdp_stream_wait() blocks until the slot's results are in page-locked host
+ * memory owned by the handle and returns pointers to them, valid until the slot is submitted again:
+ * dets = *total records of all the submission's CPIs, canonical order, cpi = index within the
+ * submission; n_dets / status per CPI.  `cube` must stay valid until the wait returns; use pinned
+ * memory (rdp_host_alloc) or the copy will not overlap.                                         */
+int rdp_stream_open(rdp_handle* h, int32_t n_slots, int32_t slot_cpis);
+int rdp_stream_submit(rdp_handle* h, int32_t slot, const void* cube, int32_t n_cpi);
+int rdp_stream_wait(rdp_handle* h, int32_t slot, const rdp_det** dets, const int32_t** n_dets,
+                    const uint32_t** status, int32_t* total);
+int rdp_stream_close(rdp_handle* h);
+
 /* Device / pinned-host memory owned by the caller (so a ctypes host needs no other CUDA binding). */
 int rdp_device_alloc(rdp_handle* h, size_t bytes, void** ptr);
 int rdp_device_free(rdp_handle* h, void* ptr);

@@ -81,3 +81,7 @@ def test_cfar_fixed_point_bit_exact(make_core, kw):
 
 def test_cfar_fixed_tb_map(make_core):
     pc.case_cfar_fixed_tb_map(make_core)
+
+
+def test_streaming(make_core):
+    pc.case_streaming(make_core)

@@ -182,6 +182,11 @@ def test_device_resident_api_matches_host_api(make_core):
         assert np.array_equal(dets, d_h) and np.array_equal(counts, n_h)
 
 
+def test_streaming(make_core):
+    pc.case_streaming(make_core)
+    pc.case_streaming(make_core, 512, 256, n_sub=5, n_slots=2)
+
+
 # ---- full-size, size-independent properties ---------------------------------------------------------
 def test_full_size_properties(make_core):
     """BASELINE config-3 shape (256 x 512 x 12 channels), 4 CPIs: determinism, exact x2 scaling
