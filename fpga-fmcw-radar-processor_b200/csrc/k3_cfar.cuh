@@ -546,26 +546,29 @@ k4_row_offsets_kernel(const uint32_t* __restrict__ det_bits, int* __restrict__ r
 
 __global__ void __launch_bounds__(256)
 k4_emit_kernel(const uint32_t* __restrict__ det_bits, const int* __restrict__ row_off, const float* __restrict__ rd_map,
-               rdp_det* __restrict__ dets, CfarArgs a, long long total_rows, int cpi_label_base) {
+               rdp_det* __restrict__ dets, CfarArgs a, long long total_rows, int cpi_label_base, int lanes_per_row) {
+    // lanes_per_row = power of two >= min(words_per_row, 32): a warp serves 32 / lanes_per_row range lines at once
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const long long row = (long long)blockIdx.x * 8 + warp;        // over (cpi, channel, range) of this launch
-    if (row >= total_rows) return;
+    const int rows_per_warp = 32 / lanes_per_row;
+    const int sub = lane % lanes_per_row;
+    const long long row = ((long long)blockIdx.x * 8 + warp) * rows_per_warp + lane / lanes_per_row;
+    const bool row_ok = row < total_rows;
     const int rows_per_cpi = a.n_channels * a.n_range;
-    const int cpi = (int)(row / rows_per_cpi), line_all = (int)(row % rows_per_cpi);
-    const uint32_t* bm = det_bits + row * a.words_per_row;
-    int base = __ldg(row_off + row);
+    const int cpi = row_ok ? (int)(row / rows_per_cpi) : 0, line_all = row_ok ? (int)(row % rows_per_cpi) : 0;
+    const uint32_t* bm = det_bits + (row_ok ? row : 0) * a.words_per_row;
+    int base = row_ok ? __ldg(row_off + row) : 0;
     rdp_det* out = dets + (long long)cpi * a.max_dets;
-    for (int w0 = 0; w0 < a.words_per_row; w0 += 32) {
-        const int w = w0 + lane;
-        uint32_t word = (w < a.words_per_row) ? __ldg(bm + w) : 0u;
+    for (int w0 = 0; w0 < a.words_per_row; w0 += lanes_per_row) {
+        const int w = w0 + sub;
+        uint32_t word = (row_ok && w < a.words_per_row) ? __ldg(bm + w) : 0u;
         const int n = __popc(word);
-        int incl = n;
-        for (int o = 1; o < 32; o <<= 1) {
+        int incl = n;                                              // inclusive scan within the line's lanes
+        for (int o = 1; o < lanes_per_row; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            if (sub >= o) incl += t;
         }
         int slot = base + incl - n;
-        base += __shfl_sync(0xffffffffu, incl, 31);
+        base += __shfl_sync(0xffffffffu, incl, (lane / lanes_per_row) * lanes_per_row + lanes_per_row - 1);
         while (word) {
             const int b = __ffs(word) - 1;
             word &= word - 1;

@@ -389,8 +389,11 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     stage_begin(h, 3);
     RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, 256, 0, h->stream, h->det_bits, h->row_off, counts, status, h->cfar);
     const long long total_rows = maps * c.n_samples;
-    RDP_LAUNCH(k4_emit_kernel, (unsigned)((total_rows + 7) / 8), 256, 0, h->stream, h->det_bits, h->row_off, rd_map, dets,
-               args, total_rows, cpi_label);
+    int lanes_per_row = 1;
+    while (lanes_per_row < args.words_per_row && lanes_per_row < 32) lanes_per_row <<= 1;
+    const long long rows_per_cta = 8ll * (32 / lanes_per_row);
+    RDP_LAUNCH(k4_emit_kernel, (unsigned)((total_rows + rows_per_cta - 1) / rows_per_cta), 256, 0, h->stream, h->det_bits,
+               h->row_off, rd_map, dets, args, total_rows, cpi_label, lanes_per_row);
     h->launches += 1;
     stage_end(h);
     return launch_check(h, "k4 compaction kernels");
