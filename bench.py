@@ -26,14 +26,23 @@ if ROOT not in sys.path:
 
 METRIC = "rd_map_os_cfar_cpis_per_sec"
 UNIT = "CPI/s"
-N_CH, N_CHIRPS, N_SAMPLES = 12, 256, 512            # BASELINE.json configs[2]: automotive MIMO
+N_CH, N_CHIRPS, N_SAMPLES = 12, 256, 512            # BASELINE.json configs[2]: automotive MIMO (the bench workload)
 CELLS = N_CH * N_CHIRPS * N_SAMPLES
+CFAR_KW = {}
+# other BASELINE configs, selectable for profiling only (--shape); the driver's bench line is `automotive`
+SHAPES = {
+    "automotive": dict(n_ch=12, n_chirps=256, n_samples=512, cfar={}, name="automotive_mimo"),
+    "rtl_native": dict(n_ch=1, n_chirps=128, n_samples=1024, cfar={}, name="rtl_native"),                 # configs[1]
+    "large": dict(n_ch=1, n_chirps=1024, n_samples=4096,                                                    # configs[3], one GPU
+                  cfar=dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2), name="large_cpi_wide_cfar"),
+}
+SHAPE_NAME = "automotive_mimo"
 # algorithmic HBM bytes per cell (SURVEY.md 8d / DESIGN.md): K1 = B_in + 8, K2 = 8 + 4, K3 = 4
 BYTES_PER_CELL = {"range": {"int16": 12, "complex64": 16}, "doppler": 12, "cfar": 4}
 
 
 def workload_name(fmt, n_cpi):
-    return f"automotive_mimo_{N_CHIRPS}x{N_SAMPLES}x{N_CH}ch_{fmt}_batch{n_cpi}"
+    return f"{SHAPE_NAME}_{N_CHIRPS}x{N_SAMPLES}x{N_CH}ch_{fmt}_batch{n_cpi}"
 
 
 def measured_peak():
@@ -103,13 +112,13 @@ def cpu_reference_step(cubes, pool=None):
     """The oracle's float path (NumPy) over `cubes`; with a pool, CPIs are spread over processes."""
     from oracle import float_path as fp
     if pool is None:
-        return [fp.process_cpi(c) for c in cubes]
+        return [fp.process_cpi(c, **CFAR_KW) for c in cubes]
     return pool.map(_cpu_one, list(cubes))
 
 
 def _cpu_one(c):
     from oracle import float_path as fp
-    m, d = fp.process_cpi(c)
+    m, d = fp.process_cpi(c, **CFAR_KW)
     return len(d)
 
 
@@ -160,7 +169,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--shape", default="automotive", choices=sorted(SHAPES), help="profiling only; default = the bench workload")
     args = ap.parse_args()
+    global N_CH, N_CHIRPS, N_SAMPLES, CELLS, CFAR_KW, SHAPE_NAME
+    sh = SHAPES[args.shape]
+    N_CH, N_CHIRPS, N_SAMPLES, CFAR_KW, SHAPE_NAME = sh["n_ch"], sh["n_chirps"], sh["n_samples"], sh["cfar"], sh["name"]
+    CELLS = N_CH * N_CHIRPS * N_SAMPLES
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +204,7 @@ def main():
     n_cpi = args.cpis
     core = rdp.RadarCore(n_range=N_SAMPLES, n_doppler=N_CHIRPS, n_channels=N_CH, input_format=args.fmt,
                          max_cpis=max(n_cpi, args.e2e_cpis), chunk_cpis=args.chunk, device=local_rank,
-                         max_dets_per_cpi=args.max_dets)
+                         max_dets_per_cpi=args.max_dets, **CFAR_KW)
     info = core.info()
 
     # ---- synthetic batch, resident in HBM before the timed region ----------------------------
@@ -329,7 +343,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args.fmt, n_cpi), "cpis_per_gpu_per_step": n_cpi,
                            "unique_cpis": int(uniq.shape[0]), "chunk_cpis": info["chunk_cpis"],
-                           "cfar": "ref 4/4 guard 2/1 rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
+                           "cfar": ("ref 8/8 guard 4/2" if CFAR_KW else "ref 4/4 guard 2/1") + " rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
                            "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),
                            "device": info["device_name"], "cfar_tile_staging": "TMA" if core.info()["cfar_tma"] else "manual", "sharding": "CPIs dealt to ranks, no data-path collective"},
                 "clocks": clocks, "e2e": e2e, "streaming": streaming, "gpu_launches": int(launches), "roofline": roofline,

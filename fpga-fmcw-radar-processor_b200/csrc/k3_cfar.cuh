@@ -75,6 +75,19 @@ __device__ __forceinline__ uint32_t bf16x2_lt_mask(uint32_t a, uint32_t b) {
     return r;
 #endif
 }
+// pre-filter reference value fl(v * s1) as float (int_mode: integer word, product rounded toward zero)
+__device__ __forceinline__ float cfar_scaled(float raw, float s1, bool int_mode) {
+    return int_mode ? __fmul_rz((float)(uint32_t)__float_as_int(raw), s1) : __fmul_rn(raw, s1);
+}
+// bfloat16 truncation of v (>= 0), duplicated into both halves of a word
+__device__ __forceinline__ uint32_t bf16_dup(float v) {
+#ifdef RDP_EMU
+    const uint32_t lo = (uint32_t)__float_as_int(v) >> 16;
+    return lo | (lo << 16);
+#else
+    return __byte_perm((uint32_t)__float_as_int(v), 0u, 0x3232);
+#endif
+}
 // float (>= 0) -> bfloat16 bits rounded toward zero / toward +inf
 __device__ __forceinline__ uint32_t bf16_down(float v) { return (uint32_t)__float_as_int(v) >> 16; }
 __device__ __forceinline__ uint32_t bf16_up(float v) { return ((uint32_t)__float_as_int(v) + 0xffffu) >> 16; }
@@ -280,11 +293,18 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         // ended the previous iteration), then wait for this tile's bytes
         if (threadIdx.x == 0 && tile_id + gridDim.x < n_tiles) issue(tile_id + gridDim.x, stage ^ 1);
         mbar_wait(mbar + stage, (uint32_t)((iter >> 1) & 1));
-        for (int i = threadIdx.x; i < Sh::SROWS * Sh::SCOLS; i += 256) {
-            // int_mode: round the product toward zero so that ref_lo never exceeds the exact integer product
-            const float fv = cfar_as_float(tf[i], INT_MODE);
-            const uint32_t lo = bf16_down(INT_MODE ? __fmul_rz(fv, a.s1) : __fmul_rn(fv, a.s1));
-            th[i] = lo | (lo << 16);
+        // raw words -> packed bf16x2 (lo, lo), four cells per thread per step (128-bit shared-memory accesses)
+        // int_mode: the product is rounded toward zero so that ref_lo never exceeds the exact integer product
+        const float4* tf4 = reinterpret_cast<const float4*>(tf);
+        uint4* th4 = reinterpret_cast<uint4*>(th);
+        for (int i = threadIdx.x; i < Sh::SROWS * Sh::SCOLS / 4; i += 256) {
+            const float4 r = tf4[i];
+            uint4 o;
+            o.x = bf16_dup(cfar_scaled(r.x, a.s1, INT_MODE));
+            o.y = bf16_dup(cfar_scaled(r.y, a.s1, INT_MODE));
+            o.z = bf16_dup(cfar_scaled(r.z, a.s1, INT_MODE));
+            o.w = bf16_dup(cfar_scaled(r.w, a.s1, INT_MODE));
+            th4[i] = o;
         }
     } else
 #endif
@@ -307,9 +327,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                         v = __ldg(m + row_base + c);
                     }
                     tf[lr * Sh::SCOLS + lc] = v;
-                    const float fv = cfar_as_float(v, INT_MODE);
-                    const uint32_t lo = bf16_down(INT_MODE ? __fmul_rz(fv, a.s1) : __fmul_rn(fv, a.s1));
-                    th[lr * Sh::SCOLS + lc] = lo | (lo << 16);
+                    th[lr * Sh::SCOLS + lc] = bf16_dup(cfar_scaled(v, a.s1, INT_MODE));
                 }
             }
         }
