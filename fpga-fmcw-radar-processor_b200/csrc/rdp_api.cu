@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -221,6 +222,10 @@ struct rdp_handle {
     int sm_count = 0;
     int chunk = 1;
     cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t cfar_stream = nullptr;    // overlap mode: K3/K4 of chunk i run here while K1/K2 of chunk i+1 run on `stream`
+    cudaStream_t cur = nullptr;            // stream the run_* helpers launch on
+    cudaEvent_t ev_map_ready[2] = {nullptr, nullptr}, ev_cfar_done[2] = {nullptr, nullptr};
+    int overlap = 1;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     std::vector<cudaEvent_t> ev_copied, ev_done, ev_mapout;
     float *win_r = nullptr, *win_d = nullptr;
@@ -300,12 +305,12 @@ void stage_begin(rdp_handle* h, int stage) {
     se.stage = stage;
     cudaEventCreate(&se.a);
     cudaEventCreate(&se.b);
-    cudaEventRecord(se.a, h->stream);
+    cudaEventRecord(se.a, h->cur);
     h->stage_events.push_back(se);
 }
 void stage_end(rdp_handle* h) {
     if (!h->stage_timing) return;
-    cudaEventRecord(h->stage_events.back().b, h->stream);
+    cudaEventRecord(h->stage_events.back().b, h->cur);
 }
 
 int launch_check(rdp_handle* h, const char* what) {
@@ -323,7 +328,7 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc) {
     if (total == 0) return RDP_OK;
     int grid = (int)(total < h->k1_grid_cap ? total : h->k1_grid_cap);
     stage_begin(h, 0);
-    h->k1.launch(grid, h->k1_smem, h->stream, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total);
+    h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total);
     stage_end(h);
     return launch_check(h, "k1_range_kernel");
 }
@@ -335,7 +340,7 @@ int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map) {
     long long blocks = (rows + h->k2.G - 1) / h->k2.G;
     int grid = (int)(blocks < h->k2_grid_cap ? blocks : h->k2_grid_cap);
     stage_begin(h, 1);
-    h->k2.launch(grid, h->k2.smem, h->stream, x_rc, rd_map, h->win_d, h->tw_d, rows, c.mti_mode);
+    h->k2.launch(grid, h->k2.smem, h->cur, x_rc, rd_map, h->win_d, h->tw_d, rows, c.mti_mode);
     stage_end(h);
     return launch_check(h, "k2_doppler_kernel");
 }
@@ -353,7 +358,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     CUtensorMap tmap;
     std::memset(&tmap, 0, sizeof(tmap));
     if (h->k3.trows == 0) {
-        h->k3.launch(maps * c.n_samples * args.words_per_row, 0, h->stream, rd_map, cfar_out, h->det_bits, args, 0, 0,
+        h->k3.launch(maps * c.n_samples * args.words_per_row, 0, h->cur, rd_map, cfar_out, h->det_bits, args, 0, 0,
                      0, 0, &tmap);
     } else {
         const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
@@ -380,19 +385,19 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
 #endif
         h->cfar_tma = use_tma;
         const long long grid = n_tiles < h->k3_grid_cap ? n_tiles : h->k3_grid_cap;
-        h->k3.launch(grid, h->k3.smem, h->stream, rd_map, cfar_out, h->det_bits, args, tiles_r, tiles_c, n_tiles, use_tma,
+        h->k3.launch(grid, h->k3.smem, h->cur, rd_map, cfar_out, h->det_bits, args, tiles_r, tiles_c, n_tiles, use_tma,
                      &tmap);
     }
     stage_end(h);
     int rc = launch_check(h, "k3_cfar_kernel");
     if (rc) return rc;
     stage_begin(h, 3);
-    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, 256, 0, h->stream, h->det_bits, h->row_off, counts, status, h->cfar);
+    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, 256, 0, h->cur, h->det_bits, h->row_off, counts, status, h->cfar);
     const long long total_rows = maps * c.n_samples;
     int lanes_per_row = 1;
     while (lanes_per_row < args.words_per_row && lanes_per_row < 32) lanes_per_row <<= 1;
     const long long rows_per_cta = 8ll * (32 / lanes_per_row);
-    RDP_LAUNCH(k4_emit_kernel, (unsigned)((total_rows + rows_per_cta - 1) / rows_per_cta), 256, 0, h->stream, h->det_bits,
+    RDP_LAUNCH(k4_emit_kernel, (unsigned)((total_rows + rows_per_cta - 1) / rows_per_cta), 256, 0, h->cur, h->det_bits,
                h->row_off, rd_map, dets, args, total_rows, cpi_label, lanes_per_row);
     h->launches += 1;
     stage_end(h);
@@ -477,6 +482,11 @@ void release(rdp_handle* h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    if (h->cfar_stream) cudaStreamDestroy(h->cfar_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_map_ready[i]) cudaEventDestroy(h->ev_map_ready[i]);
+        if (h->ev_cfar_done[i]) cudaEventDestroy(h->ev_cfar_done[i]);
+    }
     delete h;
 }
 
@@ -509,6 +519,12 @@ int init_handle(rdp_handle* h) {
     RDP_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     RDP_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     RDP_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->cfar_stream, cudaStreamNonBlocking));
+    h->cur = h->stream;
+    for (int i = 0; i < 2; ++i) {
+        RDP_CUDA(h, cudaEventCreateWithFlags(&h->ev_map_ready[i], cudaEventDefault));
+        RDP_CUDA(h, cudaEventCreateWithFlags(&h->ev_cfar_done[i], cudaEventDefault));
+    }
     RDP_CUDA(h, cudaEventCreate(&h->t0));
     RDP_CUDA(h, cudaEventCreate(&h->t1));
 
@@ -568,6 +584,16 @@ int init_handle(rdp_handle* h) {
     h->k3 = k3_for(a.half_l, a.half_c, a.guard_l, a.guard_c);
     RDP_CUDA(h, h->k3.prepare(h->k3.smem, &occ));
     h->k3_grid_cap = h->sm_count * occ;
+    {   // tuning knobs: RDP_OVERLAP=1 runs CFAR of chunk i concurrently with the FFT kernels of chunk i+1;
+        // RDP_K3_CTAS / RDP_K12_CTAS cap the persistent CTAs per SM so that both can be co-resident
+        const char* e;
+        if ((e = std::getenv("RDP_OVERLAP"))) h->overlap = std::atoi(e);
+        if ((e = std::getenv("RDP_K3_CTAS")) && std::atoi(e) > 0) h->k3_grid_cap = h->sm_count * std::atoi(e);
+        if ((e = std::getenv("RDP_K12_CTAS")) && std::atoi(e) > 0) {
+            h->k1_grid_cap = h->sm_count * std::atoi(e);
+            h->k2_grid_cap = h->sm_count * std::atoi(e);
+        }
+    }
 #ifndef RDP_EMU
     {
         cudaDriverEntryPointQueryResult qres;
@@ -583,10 +609,10 @@ int init_handle(rdp_handle* h) {
     const size_t xrc_per_cpi = cells_per_cpi(c) * sizeof(float2);
     int chunk = c.chunk_cpis;
     if (chunk == 0) {
-        // measured on B200 (profiles/r1_chunk_sweep.txt): launches of a few CPIs are dominated by ramp /
-        // tail effects, which cost more than keeping the intermediate L2-resident saves; size a chunk
-        // so that every kernel runs many waves, within 1 GiB of intermediate.
-        size_t budget = (size_t)1 << 30;
+        // measured on B200 (profiles/r1_summary.md): launches of a few CPIs are dominated by ramp / tail
+        // effects, which cost more than keeping the intermediate L2-resident saves; with the two-stream
+        // overlap of CFAR and FFT kernels the best chunk is ~32 automotive CPIs = 384 MiB of intermediate.
+        size_t budget = (size_t)384 << 20;
         chunk = (int)(budget / xrc_per_cpi);
         if (chunk < 1) chunk = 1;
         if (chunk > 256) chunk = 256;
@@ -778,6 +804,32 @@ int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd
     RDP_CUDA(h, cudaSetDevice(h->device));
     const size_t cells = cells_per_cpi(c);
     const size_t in_stride = cells * in_bytes_per_sample(c);
+    if (h->overlap && !h->stage_timing) {      // per-kernel timing wants the kernels alone on the GPU
+        // two-stream chunk pipeline: FFT kernels (HBM-bound) of chunk i+1 on `stream`, CFAR (ALU-bound) of chunk i
+        // on `cfar_stream`; the map scratch is double-buffered, det_bits / row_off belong to the CFAR stream
+        int k = 0;
+        for (int base = 0; base < n_cpi; base += h->chunk, ++k) {
+            const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
+            const int b = k & 1;
+            const unsigned char* in = reinterpret_cast<const unsigned char*>(cube) + (size_t)base * in_stride;
+            float* map = rd_map ? rd_map + (size_t)base * cells : h->map_scratch[b];
+            h->cur = h->stream;
+            if (k >= 2) RDP_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_cfar_done[b], 0));
+            int rc = run_range(h, in, n, h->x_rc);
+            if (rc) return rc;
+            rc = run_doppler(h, h->x_rc, n, map);
+            if (rc) return rc;
+            RDP_CUDA(h, cudaEventRecord(h->ev_map_ready[b], h->stream));
+            h->cur = h->cfar_stream;
+            RDP_CUDA(h, cudaStreamWaitEvent(h->cfar_stream, h->ev_map_ready[b], 0));
+            rc = run_cfar(h, map, n, nullptr, dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base);
+            h->cur = h->stream;
+            if (rc) return rc;
+            RDP_CUDA(h, cudaEventRecord(h->ev_cfar_done[b], h->cfar_stream));
+        }
+        if (k > 0) RDP_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_cfar_done[(k - 1) & 1], 0));   // rdp_sync / timers see the end
+        return RDP_OK;
+    }
     for (int base = 0; base < n_cpi; base += h->chunk) {
         const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
         const unsigned char* in = reinterpret_cast<const unsigned char*>(cube) + (size_t)base * in_stride;

@@ -82,8 +82,8 @@ typedef struct rdp_config {
     float   window_gain;       /* 1.0; 2.0 mirrors the as-built x2 of window_multiplier.vhd:146-149 */
     int32_t max_dets_per_cpi;  /* detection-list capacity per CPI                         */
     int32_t max_cpis;          /* largest n_cpi a single rdp_process* call may pass       */
-    int32_t chunk_cpis;        /* CPIs per internal pass (0 = auto: sized so the range-major
-                                  intermediate stays L2-resident between the two FFT kernels) */
+    int32_t chunk_cpis;        /* CPIs per internal pass (0 = auto: 384 MiB of range-major intermediate,
+                                  the measured optimum on B200)                            */
 } rdp_config;
 
 /* One detection = one `r d mag` record (rtl/src/tb_radar_core.vhd:153-159), with the CPI
@@ -191,7 +191,9 @@ int rdp_copy_d2h(rdp_handle* h, void* dst_host, const void* src_device, size_t b
 /* Measurement: CUDA-event timing on the handle's stream, per-stage accumulation, L2 flush. */
 int rdp_timer_start(rdp_handle* h);
 int rdp_timer_stop(rdp_handle* h, float* elapsed_ms);            /* synchronises            */
-int rdp_set_stage_timing(rdp_handle* h, int32_t enable);         /* events around each kernel */
+int rdp_set_stage_timing(rdp_handle* h, int32_t enable);         /* events around each kernel; also turns
+                                                                    off the CFAR / FFT two-stream overlap
+                                                                    so that each kernel is timed alone  */
 /* ms[0..3] = range, doppler, cfar, compaction kernels; launches[0..3] likewise; resets the sums. */
 int rdp_get_stage_timing(rdp_handle* h, float ms[4], int64_t launches[4]);
 int rdp_flush_l2(rdp_handle* h);
