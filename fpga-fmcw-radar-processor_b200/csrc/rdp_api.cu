@@ -8,6 +8,7 @@
 #include "k1_range.cuh"
 #include "k2_doppler.cuh"
 #include "k3_cfar.cuh"
+#include "k0_fixed.cuh"
 
 #ifndef RDP_EMU
 #include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through the runtime
@@ -252,6 +253,9 @@ struct rdp_handle {
     int k1_tile_chirps = 1;
     size_t k1_smem = 0;
     CfarArgs cfar;
+    int* rom_dev = nullptr;         // mirrored Q15 Hamming coefficients of the last fixed-point window length
+    int rom_n = 0;
+    uint32_t* sat_dev = nullptr;
     std::vector<StreamSlot> slots;
     int slot_cpis = 0;
     bool stage_timing = false;
@@ -477,7 +481,7 @@ void release(rdp_handle* h) {
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
-                    h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->counts, h->status, h->dets, h->packed, h->l2_flush};
+                    h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->rom_dev, h->sat_dev, h->counts, h->status, h->dets, h->packed, h->l2_flush};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -897,6 +901,83 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
     RDP_CUDA(h, cudaStreamSynchronize(h->stream));
     if (rd_map) RDP_CUDA(h, cudaStreamSynchronize(h->d2h_stream));
     return RDP_OK;
+}
+
+// ---- 16-bit fixed-point stage taps (bit-exact restatements of the hand-written RTL stages) ------------
+int rdp_fixed_window(rdp_handle* h, const void* in, int64_t n_rows, int32_t n, void* out, uint32_t* saturated) {
+    if (!h || !in || !out || n_rows < 0 || n < 2 || (n & 1)) return fail(h, RDP_E_INVALID, "rdp_fixed_window: bad argument");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    if (h->rom_n != n) {
+        // HAMMING_ROM (window_multiplier.vhd:34-49) and the mirrored address (:97-102), one coefficient per sample
+        std::vector<int> coef(n);
+        const double pi = 3.14159265358979323846;
+        const int rom_size = n / 2;
+        for (int i = 0; i < n; ++i) {
+            int a = i < rom_size ? i : n - 1 - i;
+            if (a > rom_size - 1) a = rom_size - 1;
+            long v = (long)std::floor((0.54 - 0.46 * std::cos(2.0 * pi * (double)a / (double)(n - 1))) * 32767.0 + 0.5);
+            coef[i] = (int)(v > 32767 ? 32767 : (v < 0 ? 0 : v));
+        }
+        if (h->rom_dev) { cudaFree(h->rom_dev); h->rom_dev = nullptr; }
+        int rc = dev_alloc(h, &h->rom_dev, (size_t)n);
+        if (rc) return rc;
+        RDP_CUDA(h, cudaMemcpy(h->rom_dev, coef.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+        h->rom_n = n;
+    }
+    if (!h->sat_dev) { int rc = dev_alloc(h, &h->sat_dev, 1); if (rc) return rc; }
+    RDP_CUDA(h, cudaMemsetAsync(h->sat_dev, 0, sizeof(uint32_t), h->stream));
+    const long long total = (long long)n_rows * n;
+    if (total > 0) {
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        h->launches += 1;
+        RDP_LAUNCH(kf_window_kernel, (unsigned)blocks, 256, 0, h->stream, reinterpret_cast<const uint32_t*>(in),
+                   reinterpret_cast<uint32_t*>(out), h->rom_dev, n, total, h->sat_dev);
+        int rc = launch_check(h, "kf_window_kernel");
+        if (rc) return rc;
+    }
+    if (saturated) {
+        RDP_CUDA(h, cudaMemcpyAsync(saturated, h->sat_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return RDP_OK;
+}
+
+int rdp_fixed_mti(rdp_handle* h, const void* in, int64_t n_lines, int32_t n, int32_t mode, void* out) {
+    if (!h || !in || !out || n_lines < 0 || n < 1 || (mode != 0 && mode != 2 && mode != 3))
+        return fail(h, RDP_E_INVALID, "rdp_fixed_mti: bad argument");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    const long long total = (long long)n_lines * n;
+    if (total == 0) return RDP_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    h->launches += 1;
+    RDP_LAUNCH(kf_mti_kernel, (unsigned)blocks, 256, 0, h->stream, reinterpret_cast<const uint32_t*>(in),
+               reinterpret_cast<uint32_t*>(out), n, total, mode);
+    return launch_check(h, "kf_mti_kernel");
+}
+
+int rdp_fixed_magnitude(rdp_handle* h, const void* in, int64_t n_words, uint32_t* out) {
+    if (!h || !in || !out || n_words < 0) return fail(h, RDP_E_INVALID, "rdp_fixed_magnitude: bad argument");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    if (n_words == 0) return RDP_OK;
+    long long blocks = (n_words + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    h->launches += 1;
+    RDP_LAUNCH(kf_magnitude_kernel, (unsigned)blocks, 256, 0, h->stream, reinterpret_cast<const uint32_t*>(in), out,
+               (long long)n_words);
+    return launch_check(h, "kf_magnitude_kernel");
+}
+
+int rdp_fixed_corner_turn(rdp_handle* h, const void* in, int32_t n_maps, int32_t n_chirps, int32_t n_samples, void* out) {
+    if (!h || !in || !out || n_maps < 0 || n_maps > 65535 || n_chirps < 1 || n_samples < 1)
+        return fail(h, RDP_E_INVALID, "rdp_fixed_corner_turn: bad argument");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    if (n_maps == 0) return RDP_OK;
+    h->launches += 1;
+    RDP_LAUNCH(kf_corner_turn_kernel, dim3((n_samples + 31) / 32, (n_chirps + 31) / 32, n_maps), 256, 0, h->stream,
+               reinterpret_cast<const uint32_t*>(in), reinterpret_cast<uint32_t*>(out), n_chirps, n_samples);
+    return launch_check(h, "kf_corner_turn_kernel");
 }
 
 int rdp_stream_open(rdp_handle* h, int32_t n_slots, int32_t slot_cpis) {

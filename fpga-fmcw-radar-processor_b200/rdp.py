@@ -68,6 +68,10 @@ SYMBOLS = {
     "rdp_doppler_stage": (C.c_int, [_VP, _VP, _I32, _VP]),
     "rdp_cfar_stage": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "rdp_cfar_stage_u32": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "rdp_fixed_window": (C.c_int, [_VP, _VP, C.c_int64, _I32, _VP, C.POINTER(C.c_uint32)]),
+    "rdp_fixed_mti": (C.c_int, [_VP, _VP, C.c_int64, _I32, _I32, _VP]),
+    "rdp_fixed_magnitude": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
+    "rdp_fixed_corner_turn": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP]),
     "rdp_stream_open": (C.c_int, [_VP, _I32, _I32]),
     "rdp_stream_submit": (C.c_int, [_VP, _I32, _VP, _I32]),
     "rdp_stream_wait": (C.c_int, [_VP, _I32, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_I32)]),
@@ -350,6 +354,57 @@ class RadarCore:
             for b in (d_map, d_dense, d_dets, d_counts, d_status):
                 if b is not None:
                     b.free()
+
+    # -- 16-bit fixed-point stage taps (bit-exact RTL stages; host arrays in/out) ----------------
+    def _fixed_io(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, dtype=np.int16)
+        if x.shape[-1] != 2:
+            raise RdpError(-1, "fixed-point input must be int16 [..., 2] = (I, Q)")
+        return x, self.device_buffer(x.nbytes).upload(x), self.device_buffer(max(x.nbytes, 16))
+
+    def fixed_window(self, x: np.ndarray):
+        """window_multiplier along the second-to-last axis' rows: x int16 [..., n, 2] -> (y int16, saturated bool)."""
+        x, d_in, d_out = self._fixed_io(x)
+        n = x.shape[-2]
+        sat = C.c_uint32(0)
+        try:
+            self._check(self.lib.rdp_fixed_window(self.h, d_in.ptr, x.size // (2 * n), n, d_out.ptr, C.byref(sat)))
+            self.sync()
+            return d_out.download(x.shape, np.int16), bool(sat.value)
+        finally:
+            d_in.free(); d_out.free()
+
+    def fixed_mti(self, x: np.ndarray, mode: int = 2) -> np.ndarray:
+        """doppler_notch along lines: x int16 [..., n, 2] -> y int16."""
+        x, d_in, d_out = self._fixed_io(x)
+        n = x.shape[-2]
+        try:
+            self._check(self.lib.rdp_fixed_mti(self.h, d_in.ptr, x.size // (2 * n), n, mode, d_out.ptr))
+            self.sync()
+            return d_out.download(x.shape, np.int16)
+        finally:
+            d_in.free(); d_out.free()
+
+    def fixed_magnitude(self, x: np.ndarray) -> np.ndarray:
+        """magnitude_calc: x int16 [..., 2] -> uint32 [...]."""
+        x, d_in, d_out = self._fixed_io(x)
+        try:
+            self._check(self.lib.rdp_fixed_magnitude(self.h, d_in.ptr, x.size // 2, d_out.ptr))
+            self.sync()
+            return d_out.download(x.shape[:-1], np.uint32)
+        finally:
+            d_in.free(); d_out.free()
+
+    def fixed_corner_turn(self, x: np.ndarray) -> np.ndarray:
+        """corner_turner: x int16 [map, chirp, sample, 2] -> [map, range, chirp, 2]."""
+        x, d_in, d_out = self._fixed_io(x)
+        n_maps, n_chirps, n_samples = x.shape[0], x.shape[1], x.shape[2]
+        try:
+            self._check(self.lib.rdp_fixed_corner_turn(self.h, d_in.ptr, n_maps, n_chirps, n_samples, d_out.ptr))
+            self.sync()
+            return d_out.download((n_maps, n_samples, n_chirps, 2), np.int16)
+        finally:
+            d_in.free(); d_out.free()
 
     # -- streaming ingest (BASELINE config 5) -------------------------------------------------
     def stream_open(self, n_slots: int = 3, slot_cpis: int = 1):

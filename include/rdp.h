@@ -165,6 +165,23 @@ int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfa
 int rdp_cfar_stage_u32(rdp_handle* h, const uint32_t* mag_map, int32_t n_cpi, uint32_t* cfar_out,
                        rdp_det* dets, int32_t* n_dets, uint32_t* status);
 
+/* 16-bit fixed-point stage taps on DEVICE buffers: bit-exact restatements of the hand-written RTL
+ * stages (the FFT IP's arithmetic is not defined in the reference tree, so K1/K2 stay float32).
+ * A sample is the 32-bit stream word {Q[31:16], I[15:0]} = int16 I then int16 Q in memory.
+ *   rdp_fixed_window      window_multiplier (rtl/src/window_multiplier.vhd:34-49,97-158) along rows of n
+ *                         words: y = sat16((x * coef + 2^14) >> 14); *saturated (host, nullable) = the
+ *                         sticky saturation_flag
+ *   rdp_fixed_mti         doppler_notch (rtl/src/doppler_notch.vhd:70-104) along lines of n words,
+ *                         mode 0 = bypass, 2, 3
+ *   rdp_fixed_magnitude   magnitude_calc (rtl/src/magnitude_calc.vhd:55-81): word -> 17-bit unsigned
+ *   rdp_fixed_corner_turn corner_turner (rtl/src/corner_turner.vhd:79-80): [map][chirp][sample] ->
+ *                         [map][range][chirp] of 32-bit words                                       */
+int rdp_fixed_window(rdp_handle* h, const void* in, int64_t n_rows, int32_t n, void* out, uint32_t* saturated);
+int rdp_fixed_mti(rdp_handle* h, const void* in, int64_t n_lines, int32_t n, int32_t mode, void* out);
+int rdp_fixed_magnitude(rdp_handle* h, const void* in, int64_t n_words, uint32_t* out);
+int rdp_fixed_corner_turn(rdp_handle* h, const void* in, int32_t n_maps, int32_t n_chirps, int32_t n_samples,
+                          void* out);
+
 /* Streaming ingest (BASELINE config 5: pinned-host, multi-buffered chirp ingest).  n_slots
  * submissions may be in flight; each carries up to slot_cpis CPIs (<= the handle's chunk size).
  * rdp_stream_submit() is asynchronous: the host->device copy of submission i+1 overlaps the

@@ -247,3 +247,49 @@ def case_streaming(make_core, n_samples=64, n_chirps=32, n_sub=7, n_slots=3):
         for f in ("channel", "range", "doppler", "mag"):
             assert np.array_equal(d[f], exp[f])
         assert np.all(d["cpi"] == 0)
+
+
+def case_fixed_stages(make_core):
+    """16-bit fixed-point stage taps against the bit-exact oracle AND the reference's own testbench vectors."""
+    from test_oracle_fixed import MAG_VECTORS, MAG_EXPECTED
+    rng = np.random.default_rng(17)
+    with make_core(n_range=64, n_doppler=32) as c:
+        # magnitude: the 17 known answers of rtl/src/tb_magnitude_calc.vhd:49-73, exact (+ extremes)
+        vec = np.array(MAG_VECTORS + [(-32768, -32768), (-32768, 0)], dtype=np.int16)
+        got = c.fixed_magnitude(vec)
+        assert got.tolist() == MAG_EXPECTED + [32768 + 8192 + 4096, 32768]
+        z = rng.integers(-32768, 32768, size=(1000, 2)).astype(np.int16)
+        assert np.array_equal(c.fixed_magnitude(z), fx.magnitude(z[:, 0], z[:, 1]))
+        # corner turn: rtl/src/tb_corner_turner.vhd:36-39,146-186 (16 x 8, value = chirp * 256 + sample)
+        chirp, sample = np.arange(8)[:, None], np.arange(16)[None, :]
+        val = (chirp * 256 + sample).astype(np.int16)
+        x = np.stack([val, -val], axis=-1)[None]
+        y = c.fixed_corner_turn(x)
+        assert y.shape == (1, 16, 8, 2)
+        flat = y[0, :, :, 0].reshape(-1).astype(np.int64)
+        assert np.array_equal(flat // 256, np.tile(np.arange(8), 16)) and np.array_equal(flat % 256, np.repeat(np.arange(16), 8))
+        big = rng.integers(-32768, 32768, size=(3, 70, 45, 2)).astype(np.int16)
+        assert np.array_equal(c.fixed_corner_turn(big), np.swapaxes(big, 1, 2))
+        # window: rtl/src/tb_window_multiplier.vhd:83-108,185-240 (N = 64) + random rows vs the oracle
+        dc = np.full((1, 64, 2), 16000, np.int16)
+        y, sat = c.fixed_window(dc)
+        assert not sat and abs(int(y[0, 0, 0])) <= 3000 and int(y[0, 32, 0]) >= 10000
+        assert np.all(np.abs(y[0, :, 0].astype(int) - y[0, ::-1, 0].astype(int)) <= 1)
+        y, sat = c.fixed_window(np.full((1, 64, 2), 32767, np.int16))
+        assert sat and int(y.max()) == 32767
+        y, sat = c.fixed_window(np.zeros((1, 64, 2), np.int16))
+        assert np.all(y == 1)                                # as-built rounding constant (window_multiplier.vhd:146-149)
+        for n in (64, 256, 1024):
+            w = rng.integers(-32768, 32768, size=(5, n, 2)).astype(np.int16)
+            y, sat = c.fixed_window(w)
+            ei, si = fx.window(w[..., 0], n)
+            eq, sq = fx.window(w[..., 1], n)
+            assert np.array_equal(y[..., 0], ei) and np.array_equal(y[..., 1], eq) and sat == bool(si.any() or sq.any())
+        # MTI: rtl/src/tb_doppler_notch.vhd:117-180 + random lines vs the oracle
+        line = np.full((2, 32, 2), 5000, np.int16)
+        y = c.fixed_mti(line, 2)
+        assert np.all(y[:, 0] == 5000) and np.all(y[:, 1:] == 0)
+        for mode in (0, 2, 3):
+            w = rng.integers(-32768, 32768, size=(7, 33, 2)).astype(np.int16)
+            y = c.fixed_mti(w, mode)
+            assert np.array_equal(y[..., 0], fx.mti(w[..., 0], mode)) and np.array_equal(y[..., 1], fx.mti(w[..., 1], mode))

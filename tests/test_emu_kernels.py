@@ -85,3 +85,7 @@ def test_cfar_fixed_tb_map(make_core):
 
 def test_streaming(make_core):
     pc.case_streaming(make_core)
+
+
+def test_fixed_stages(make_core):
+    pc.case_fixed_stages(make_core)

@@ -113,6 +113,10 @@ def test_cfar_fixed_rejects_untiled_window(make_core):
             c.cfar_stage_fixed(np.ones((1, 1, 64, 64), np.uint32))
 
 
+def test_fixed_stages(make_core):
+    pc.case_fixed_stages(make_core)
+
+
 # ---- whole path ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_cpi,n_ch,nc,ns,fmt,kw", [
     (2, 3, 256, 512, "int16", dict()),                                   # BASELINE config 3 shape
