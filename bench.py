@@ -270,6 +270,12 @@ def main():
                 "traffic": ncu_traffic(kernel_names[dom], n_cpi / max(1, stages[dom]["launches_per_step"])),
                 "algorithmic_bytes_per_launch": stages[dom]["alg_bytes_per_cell"] * CELLS * n_cpi / max(1, stages[dom]["launches_per_step"]),
                 "peak_source": peak_src, "stages": stages,
+                # K3 is bounded by compare throughput, not bytes: mandatory (cell, reference) comparisons per second
+                # against the best packed-compare rate measured on this GPU (profiles/r1_mb_cmpacc_b200.txt)
+                "cfar_compare_roofline": ({"achieved_gcompare_s": 128.0 * n_cpi * CELLS / (stages["cfar"]["ms_total_per_step"] * 1e-3) / 1e9,
+                                           "peak_gcompare_s": 39311.0, "unit": "Gcompare/s",
+                                           "frac": 128.0 * n_cpi * CELLS / (stages["cfar"]["ms_total_per_step"] * 1e-3) / 1e9 / 39311.0}
+                                          if "cfar" in stages and not CFAR_KW else None),
                 "note": "K3 (OS-CFAR, 128 reference cells per cell) is ALU-bound, not HBM-bound; see DESIGN.md"}
 
     # ---- end to end: pinned host cube in, detection list out, copies inside the timed region --
