@@ -78,24 +78,26 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
     // software pipeline: the raw samples of the NEXT chirp this group transforms are in flight while the
     // current one is in the butterflies
     typename Raw::T raw[E];
-    auto fetch = [&](long long t, int it) {
+    const int n_tiles = (int)total_tiles;                  // < 2^31 (checked by the host): 32-bit index arithmetic
+    auto fetch = [&](int t, int it) {
         const int c = it * G + gid;
-        const bool ok = t < total_tiles && c < tile_chirps;
-        const long long map = t / tiles_per_map;
-        const int c0 = (int)(t % tiles_per_map) * tile_chirps;
-        const long long base = ((map * n_chirps) + c0 + c) * (long long)N;
+        const bool ok = t < n_tiles && c < tile_chirps;
+        const int mp = t / tiles_per_map;
+        const int chirp = mp * n_chirps + (t - mp * tiles_per_map) * tile_chirps + c;     // global chirp index
+        const long long first = (long long)chirp * N + tid;
         RDP_UNROLL
         for (int b = 0; b < P0::NB; ++b) {
             RDP_UNROLL
             for (int r = 0; r < P0::R; ++r)
-                raw[b * P0::R + r] = ok ? Raw::load(cube, base + P0::in_index(tid, b, r)) : Raw::zero();
+                raw[b * P0::R + r] = ok ? Raw::load(cube, first + (b * T + r * (N / P0::R))) : Raw::zero();
         }
     };
-    fetch(blockIdx.x, 0);
+    fetch((int)blockIdx.x, 0);
 
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const long long map = t / tiles_per_map;
-        const int c0 = (int)(t % tiles_per_map) * tile_chirps;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int mp = t / tiles_per_map;
+        const long long map = mp;
+        const int c0 = (t - mp * tiles_per_map) * tile_chirps;
         for (int it = 0; it < iters; ++it) {
             const int c = it * G + gid;
             const bool active = c < tile_chirps;
@@ -106,7 +108,7 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
                 v[i] = make_float2(s.x * wv[i], s.y * wv[i]);
             }
             if (it + 1 < iters) fetch(t, it + 1);
-            else fetch(t + gridDim.x, 0);
+            else fetch(t + (int)gridDim.x, 0);
             Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
             if (active) {
                 RDP_UNROLL
@@ -119,10 +121,21 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
         __syncthreads();
         // range-major store: row k of the tile -> x_rc[map][k][c0 .. c0+tile_chirps)
         float2* dst = x_rc + map * (long long)N * n_chirps + c0;
-        if (tile_chirps == TCM) {                          // compile-time tile width: no integer division
-            const int c = threadIdx.x % TCM;
-            for (int k = threadIdx.x / TCM; k < N; k += THREADS / TCM)
-                dst[(long long)k * n_chirps + c] = tile[k * (TCM + 1) + c];
+        if (tile_chirps == TCM && (TCM % 2) == 0 && (n_chirps % 2) == 0) {
+            // compile-time tile width: each thread moves two adjacent chirps of one range bin per step with one
+            // 128-bit store (rows of the output are 16-byte aligned: c0, n_chirps even); pointers just advance
+            constexpr int HALF = TCM / 2, KSTEP = THREADS / HALF;
+            const int c = (threadIdx.x % HALF) * 2;
+            int k = threadIdx.x / HALF;
+            const float2* src = tile + k * (TCM + 1) + c;
+            float4* out = reinterpret_cast<float4*>(dst + (long long)k * n_chirps + c);
+            const long long ostep = (long long)KSTEP * n_chirps / 2;
+            for (; k < N; k += KSTEP) {
+                const float2 a = src[0], b2 = src[1];
+                *out = make_float4(a.x, a.y, b2.x, b2.y);
+                src += KSTEP * (TCM + 1);
+                out += ostep;
+            }
         } else {
             const int total = N * tile_chirps;
             for (int i = threadIdx.x; i < total; i += THREADS) {

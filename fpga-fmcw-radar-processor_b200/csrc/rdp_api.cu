@@ -330,6 +330,8 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc) {
     const int tiles_per_map = c.n_chirps / tc;
     const long long total = (long long)n_cpi * c.n_channels * tiles_per_map;
     if (total == 0) return RDP_OK;
+    if (total >= (1ll << 31) || (long long)n_cpi * c.n_channels * c.n_chirps >= (1ll << 31))
+        return fail(h, RDP_E_CAPACITY, "range stage: too many chirps in one launch; lower chunk_cpis");
     int grid = (int)(total < h->k1_grid_cap ? total : h->k1_grid_cap);
     stage_begin(h, 0);
     h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total);
