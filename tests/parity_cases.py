@@ -293,3 +293,38 @@ def case_fixed_stages(make_core):
             w = rng.integers(-32768, 32768, size=(7, 33, 2)).astype(np.int16)
             y = c.fixed_mti(w, mode)
             assert np.array_equal(y[..., 0], fx.mti(w[..., 0], mode)) and np.array_equal(y[..., 1], fx.mti(w[..., 1], mode))
+
+
+def case_cfar_random_config(make_core, seed):
+    """Randomised CFAR generics (window extents, guard, rank, scales, override, edge rule, axis convention) on a
+    random map: float CUDA CFAR bit-exact against the float oracle, fixed-point CUDA CFAR bit-exact against the
+    integer oracle whenever the window shape has a tiled kernel."""
+    rng = np.random.default_rng(seed)
+    tiled = [(4, 4, 2, 1), (3, 2, 1, 1), (2, 2, 1, 1), (8, 8, 4, 2)]
+    if rng.random() < 0.5:
+        rr, rd, gr, gd = tiled[int(rng.integers(0, len(tiled)))]
+    else:
+        rr, rd, gr, gd = int(rng.integers(1, 4)), int(rng.integers(1, 4)), int(rng.integers(0, 3)), int(rng.integers(0, 3))
+    smin = int(rng.integers(1, 4))
+    kw = dict(cfar_ref_r=rr, cfar_ref_d=rd, cfar_guard_r=gr, cfar_guard_d=gd, rank_pct=int(rng.integers(10, 100)),
+              scale_min=smin, scale_nom=smin + int(rng.integers(0, 3)), scale_max=smin + int(rng.integers(2, 5)),
+              scale_override=int(rng.choice([0, 0, 0, 1, 3, 7])), cfar_edges=str(rng.choice(["zero", "raster"])),
+              cfar_axes=str(rng.choice(["as_built", "as_named"])))
+    nr, nd = int(rng.choice([8, 16, 32, 64])), int(rng.choice([8, 16, 32, 64, 128]))
+    m = rng.rayleigh(60.0, size=(2, nr, nd)).astype(np.float32)
+    for _ in range(3):
+        m[int(rng.integers(0, 2)), int(rng.integers(0, nr)), int(rng.integers(0, nd))] = float(rng.uniform(500, 5000))
+    m[0, 0, :] *= 3.0
+    with make_core(n_range=nr, n_doppler=nd, n_channels=2, max_dets_per_cpi=1 << 15, **kw) as c:
+        dets, counts, status, dense = c.cfar_stage(m[None])
+        exp = np.stack([fp.cfar_stage(m[i], **kw) for i in range(2)])
+        assert np.array_equal(dense[0], exp), kw
+        assert counts[0] == np.count_nonzero(exp)
+        if (rr, rd, gr, gd) in tiled:
+            mi = np.minimum(m * 8.0, 131071.0).astype(np.uint32)
+            d2, c2, s2, dense_i = c.cfar_stage_fixed(mi[None])
+            names = dict(cfar_ref_r="ref_range", cfar_ref_d="ref_doppler", cfar_guard_r="guard_range",
+                         cfar_guard_d="guard_doppler", cfar_edges="edges", cfar_axes="axes")
+            okw = {names.get(k, k): v for k, v in kw.items()}
+            exp_i = np.stack([fx.os_cfar_2d(mi[i], **okw) for i in range(2)])
+            assert np.array_equal(dense_i[0], exp_i), kw

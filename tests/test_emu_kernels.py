@@ -89,3 +89,8 @@ def test_streaming(make_core):
 
 def test_fixed_stages(make_core):
     pc.case_fixed_stages(make_core)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cfar_random_config(make_core, seed):
+    pc.case_cfar_random_config(make_core, 1000 + seed)

@@ -113,6 +113,11 @@ def test_cfar_fixed_rejects_untiled_window(make_core):
             c.cfar_stage_fixed(np.ones((1, 1, 64, 64), np.uint32))
 
 
+@pytest.mark.parametrize("seed", range(40))
+def test_cfar_random_config(make_core, seed):
+    pc.case_cfar_random_config(make_core, seed)
+
+
 def test_fixed_stages(make_core):
     pc.case_fixed_stages(make_core)
 
