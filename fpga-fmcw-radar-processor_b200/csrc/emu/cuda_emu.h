@@ -172,6 +172,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __reduce_add_sync(unsigned m, int v) {
     for (int o = 16; o > 0; o >>= 1) {

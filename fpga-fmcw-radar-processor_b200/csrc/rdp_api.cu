@@ -9,6 +9,7 @@
 #include "k2_doppler.cuh"
 #include "k3_cfar.cuh"
 #include "k0_fixed.cuh"
+#include "k6_tracker.cuh"
 
 #ifndef RDP_EMU
 #include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through the runtime
@@ -253,6 +254,8 @@ struct rdp_handle {
     int k1_tile_chirps = 1;
     size_t k1_smem = 0;
     CfarArgs cfar;
+    TrackState* trk_state = nullptr;   // one track file per channel
+    TrackerArgs trk_args;
     int* rom_dev = nullptr;         // mirrored Q15 Hamming coefficients of the last fixed-point window length
     int rom_n = 0;
     uint32_t* sat_dev = nullptr;
@@ -483,7 +486,7 @@ void release(rdp_handle* h) {
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
-                    h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->rom_dev, h->sat_dev, h->counts, h->status, h->dets, h->packed, h->l2_flush};
+                    h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->rom_dev, h->sat_dev, h->trk_state, h->counts, h->status, h->dets, h->packed, h->l2_flush};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -980,6 +983,38 @@ int rdp_fixed_corner_turn(rdp_handle* h, const void* in, int32_t n_maps, int32_t
     RDP_LAUNCH(kf_corner_turn_kernel, dim3((n_samples + 31) / 32, (n_chirps + 31) / 32, n_maps), 256, 0, h->stream,
                reinterpret_cast<const uint32_t*>(in), reinterpret_cast<uint32_t*>(out), n_chirps, n_samples);
     return launch_check(h, "kf_corner_turn_kernel");
+}
+
+int rdp_tracker_reset(rdp_handle* h, const rdp_tracker_config* cfg) {
+    if (!h) return RDP_E_INVALID;
+    rdp_tracker_config d = {32, 2, 5, 10, 5, 128, 64};          // radar_core.vhd:425-429
+    if (cfg) d = *cfg;
+    if (d.max_tracks < 1 || d.max_tracks > 32 || d.init_hits < 0 || d.coast_max < 0 || d.assoc_gate_r < 0 || d.assoc_gate_d < 0)
+        return fail(h, RDP_E_INVALID, "rdp_tracker_reset: bad generics (max_tracks must be 1..32)");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    const int n_ch = h->cfg.n_channels;
+    if (!h->trk_state) { int rc = dev_alloc(h, &h->trk_state, (size_t)n_ch); if (rc) return rc; }
+    std::vector<TrackState> init((size_t)n_ch);
+    std::memset(init.data(), 0, sizeof(TrackState) * (size_t)n_ch);
+    for (auto& s : init) { s.best_det_idx = 63; s.best_distance = 0xffff; }      // signal initialisers, tws_tracker.vhd:81-83
+    RDP_CUDA(h, cudaMemcpyAsync(h->trk_state, init.data(), sizeof(TrackState) * (size_t)n_ch, cudaMemcpyHostToDevice, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->trk_args = TrackerArgs{d.max_tracks, d.init_hits, d.coast_max, d.assoc_gate_r, d.assoc_gate_d, d.alpha_gain, d.beta_gain,
+                              n_ch, h->cfg.max_dets_per_cpi};
+    return RDP_OK;
+}
+
+int rdp_track_device(rdp_handle* h, const rdp_det* dets, const int32_t* n_dets, int32_t n_cpi, rdp_track* tracks,
+                     int32_t* n_tracks, int32_t* active) {
+    if (!h || !dets || !n_dets || !tracks || !n_tracks || !active || n_cpi < 0)
+        return fail(h, RDP_E_INVALID, "rdp_track_device: bad argument");
+    if (!h->trk_state) { int rc = rdp_tracker_reset(h, nullptr); if (rc) return rc; }
+    if (n_cpi == 0) return RDP_OK;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    h->launches += 1;
+    RDP_LAUNCH(k6_tracker_kernel, h->cfg.n_channels, 32, 0, h->stream, dets, n_dets, n_cpi, h->trk_args, h->trk_state, tracks,
+               n_tracks, active, 0);
+    return launch_check(h, "k6_tracker_kernel");
 }
 
 int rdp_stream_open(rdp_handle* h, int32_t n_slots, int32_t slot_cpis) {

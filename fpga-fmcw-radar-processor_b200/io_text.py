@@ -34,3 +34,18 @@ def read_detections(path) -> np.ndarray:
             except ValueError:
                 continue
     return np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+
+
+def write_tracks(path, tracks, active, channel=0) -> int:
+    """The reference's track log (rtl/src/tb_radar_core.vhd:163-181, parsed by model/ADR_visualize.py:124-168):
+    `TRK <id> R=<range q2> D=<doppler q2> Q=<quality>` per reported track and `SCAN_END ACTIVE=<n>` per scan, for
+    one channel.  `tracks` / `active` as returned by RadarCore.track().  Returns the number of lines."""
+    n = 0
+    with open(path, "w") as f:
+        for cpi in range(active.shape[0]):
+            for t in tracks[(tracks["cpi"] == cpi) & (tracks["channel"] == channel)]:
+                f.write(f"TRK {int(t['id'])} R={int(t['range_q2'])} D={int(t['doppler_q2'])} Q={int(t['quality'])}\n")
+                n += 1
+            f.write(f"SCAN_END ACTIVE={int(active[cpi, channel])}\n")
+            n += 1
+    return n

@@ -29,6 +29,11 @@ MAG_MODES = {"amb": 0, "abs": 1, "pow": 2, "logpow": 3}
 CFAR_AXES = {"as_built": 0, "as_named": 1}
 CFAR_EDGES = {"zero": 0, "raster": 1}
 
+# one reported track; layout == struct rdp_track
+TRACK_DTYPE = np.dtype([(n, "<i4") for n in ("cpi", "channel", "id", "range_q2", "doppler_q2", "vel_r", "vel_d",
+                                              "quality", "status")])
+TRACK_FIRM, TRACK_COAST = 2, 3
+
 # one `r d mag` record (+ CPI, channel); layout == struct rdp_det
 DET_DTYPE = np.dtype([("cpi", "<i4"), ("channel", "<i4"), ("range", "<i4"), ("doppler", "<i4"), ("mag", "<f4")])
 
@@ -45,6 +50,11 @@ class RdpConfig(C.Structure):
         "cfar_guard_d", "rank_pct", "scale_min", "scale_nom", "scale_max", "scale_override", "mti_mode",
         "input_format", "mag_mode", "cfar_axes", "cfar_edges")] + [("window_gain", C.c_float)] + [
         (n, C.c_int32) for n in ("max_dets_per_cpi", "max_cpis", "chunk_cpis")]
+
+
+class RdpTrackerConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("max_tracks", "init_hits", "coast_max", "assoc_gate_r", "assoc_gate_d",
+                                         "alpha_gain", "beta_gain")]
 
 
 class RdpInfo(C.Structure):
@@ -72,6 +82,8 @@ SYMBOLS = {
     "rdp_fixed_mti": (C.c_int, [_VP, _VP, C.c_int64, _I32, _I32, _VP]),
     "rdp_fixed_magnitude": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "rdp_fixed_corner_turn": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP]),
+    "rdp_tracker_reset": (C.c_int, [_VP, C.POINTER(RdpTrackerConfig)]),
+    "rdp_track_device": (C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
     "rdp_stream_open": (C.c_int, [_VP, _I32, _I32]),
     "rdp_stream_submit": (C.c_int, [_VP, _I32, _VP, _I32]),
     "rdp_stream_wait": (C.c_int, [_VP, _I32, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_I32)]),
@@ -354,6 +366,42 @@ class RadarCore:
             for b in (d_map, d_dense, d_dets, d_counts, d_status):
                 if b is not None:
                     b.free()
+
+    # -- track-while-scan processor (tws_tracker) on the detection list -------------------------
+    def tracker_reset(self, max_tracks=32, init_hits=2, coast_max=5, assoc_gate_r=10, assoc_gate_d=5,
+                      alpha_gain=128, beta_gain=64):
+        """aresetn of every tracker instance (one per channel); generics as radar_core.vhd:425-429."""
+        cfg = RdpTrackerConfig(max_tracks, init_hits, coast_max, assoc_gate_r, assoc_gate_d, alpha_gain, beta_gain)
+        self._check(self.lib.rdp_tracker_reset(self.h, C.byref(cfg)))
+
+    def track(self, dets: np.ndarray, n_dets: np.ndarray):
+        """One scan per CPI, one tracker per channel: `dets` = the canonical list process() returns (CPI indices
+        0..n_cpi-1), `n_dets` its per-CPI counts.  -> (tracks TRACK_DTYPE in (cpi, channel, id) order,
+        n_tracks int32 [cpi, channel], active int32 [cpi, channel]).  Track files persist between calls."""
+        n_dets = np.ascontiguousarray(n_dets, dtype=np.int32)
+        n_cpi = n_dets.size
+        kept = np.minimum(n_dets, self.max_dets_per_cpi)
+        rows = np.zeros((n_cpi, self.max_dets_per_cpi), dtype=DET_DTYPE)
+        off = 0
+        for i in range(n_cpi):
+            rows[i, :kept[i]] = dets[off:off + kept[i]]
+            off += int(kept[i])
+        n_ch = self.n_channels
+        d_dets = self.device_buffer(rows.nbytes).upload(rows)
+        d_cnt = self.device_buffer(max(n_cpi * 4, 16)).upload(n_dets)
+        d_trk = self.device_buffer(max(n_cpi * n_ch * 32 * TRACK_DTYPE.itemsize, 16))
+        d_nt, d_act = self.device_buffer(max(n_cpi * n_ch * 4, 16)), self.device_buffer(max(n_cpi * n_ch * 4, 16))
+        try:
+            self._check(self.lib.rdp_track_device(self.h, d_dets.ptr, d_cnt.ptr, n_cpi, d_trk.ptr, d_nt.ptr, d_act.ptr))
+            self.sync()
+            trk = d_trk.download((n_cpi, n_ch, 32), TRACK_DTYPE)
+            nt = d_nt.download((n_cpi, n_ch), np.int32)
+            act = d_act.download((n_cpi, n_ch), np.int32)
+            out = [trk[i, c, :nt[i, c]] for i in range(n_cpi) for c in range(n_ch)]
+            return (np.concatenate(out) if out else np.zeros(0, TRACK_DTYPE)), nt, act
+        finally:
+            for b in (d_dets, d_cnt, d_trk, d_nt, d_act):
+                b.free()
 
     # -- 16-bit fixed-point stage taps (bit-exact RTL stages; host arrays in/out) ----------------
     def _fixed_io(self, x: np.ndarray):

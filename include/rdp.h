@@ -97,6 +97,31 @@ typedef struct rdp_det {
     float   mag;
 } rdp_det;
 
+/* One reported track = one `TRK <id> R=<q2> D=<q2> Q=<quality>` line (rtl/src/tb_radar_core.vhd:163-181):
+ * the trk_* outputs of rtl/src/tws_tracker.vhd:30-37; positions are Q2 (bins * 4) signed as in the RTL. */
+typedef struct rdp_track {
+    int32_t cpi;
+    int32_t channel;
+    int32_t id;
+    int32_t range_q2;
+    int32_t doppler_q2;
+    int32_t vel_r;
+    int32_t vel_d;
+    int32_t quality;
+    int32_t status;            /* 2 = FIRM, 3 = COAST (only these are reported, tws_tracker.vhd:280-281) */
+} rdp_track;
+
+/* generics of tws_tracker (rtl/src/tws_tracker.vhd:10-20) as radar_core sets them (radar_core.vhd:425-429) */
+typedef struct rdp_tracker_config {
+    int32_t max_tracks;        /* MAX_TRACKS (<= 32)          default 32  */
+    int32_t init_hits;         /* INIT_HITS                   default 2   */
+    int32_t coast_max;         /* COAST_MAX                   default 5   */
+    int32_t assoc_gate_r;      /* ASSOC_GATE_R (bins)         default 10  */
+    int32_t assoc_gate_d;      /* ASSOC_GATE_D (bins)         default 5   */
+    int32_t alpha_gain;        /* ALPHA_GAIN (Q8)             default 128 */
+    int32_t beta_gain;         /* BETA_GAIN (Q8)              default 64  */
+} rdp_tracker_config;
+
 typedef struct rdp_info {
     int32_t abi_version;
     int32_t device;
@@ -196,6 +221,19 @@ int rdp_stream_submit(rdp_handle* h, int32_t slot, const void* cube, int32_t n_c
 int rdp_stream_wait(rdp_handle* h, int32_t slot, const rdp_det** dets, const int32_t** n_dets,
                     const uint32_t** status, int32_t* total);
 int rdp_stream_close(rdp_handle* h);
+
+/* Track-while-scan processor on the DEVICE detection list (the consumer of the path: tws_tracker in
+ * rtl/src/radar_core.vhd:424-439), bit-exact with rtl/src/tws_tracker.vhd including its as-built
+ * signal-semantics behaviour.  One tracker instance per channel; one scan per CPI (the RTL's top level
+ * ends a scan at every range line's tlast, radar_core.vhd:434 -- a wiring defect that is not reproduced).
+ *   rdp_tracker_reset  (re)initialise every instance (aresetn); cfg NULL = the radar_core generics
+ *   rdp_track_device   dets / n_dets as produced by rdp_process_device for n_cpi CPIs (device pointers);
+ *                      tracks [n_cpi][channel][32] records, n_tracks [n_cpi][channel] reported per scan,
+ *                      active [n_cpi][channel] = active_tracks after the scan (all device pointers).
+ *                      Track files persist between calls.                                           */
+int rdp_tracker_reset(rdp_handle* h, const rdp_tracker_config* cfg);
+int rdp_track_device(rdp_handle* h, const rdp_det* dets, const int32_t* n_dets, int32_t n_cpi, rdp_track* tracks,
+                     int32_t* n_tracks, int32_t* active);
 
 /* Device / pinned-host memory owned by the caller (so a ctypes host needs no other CUDA binding). */
 int rdp_device_alloc(rdp_handle* h, size_t bytes, void** ptr);

@@ -328,3 +328,77 @@ def case_cfar_random_config(make_core, seed):
             okw = {names.get(k, k): v for k, v in kw.items()}
             exp_i = np.stack([fx.os_cfar_2d(mi[i], **okw) for i in range(2)])
             assert np.array_equal(dense_i[0], exp_i), kw
+
+
+def _dets_from_scans(scans_per_channel):
+    """scans_per_channel[cpi][channel] = list of (r, d, mag) in (range, doppler) order -> canonical list + counts."""
+    import fpga_fmcw_radar_processor_b200 as rdp
+    rows, counts = [], []
+    for cpi, chans in enumerate(scans_per_channel):
+        n = 0
+        for ch, lst in enumerate(chans):
+            for (r, d, mag) in lst:
+                rows.append((cpi, ch, r, d, float(mag)))
+                n += 1
+        counts.append(n)
+    dets = np.zeros(len(rows), dtype=rdp.DET_DTYPE)
+    for i, r in enumerate(rows):
+        dets[i] = r
+    return dets, np.asarray(counts, np.int32)
+
+
+def case_tracker(make_core):
+    """tws_tracker on the device detection list against the bit-exact oracle (oracle/tracker.py): the scripted
+    scenario of rtl/src/tb_tws_tracker.vhd (with its assertions), then random multi-channel scans including more
+    than 64 detections per scan (the 6-bit det_count wrap) and state carried across two calls."""
+    from oracle import tracker as tk
+    from test_oracle_tracker import tb_scan_detections
+    # --- the reference testbench scenario, generics of tb_tws_tracker.vhd:11-18
+    scans = [[sorted(tb_scan_detections(s))] for s in range(1, 13)]
+    dets, counts = _dets_from_scans(scans)
+    with make_core(n_range=1024, n_doppler=128, max_cpis=12) as c:
+        c.tracker_reset(max_tracks=16, coast_max=3)
+        trk, nt, act = c.track(dets, counts)
+    ref = tk.TwsTracker(max_tracks=16, coast_max=3)
+    exp_rows, exp_act = [], []
+    for cpi, s in enumerate(scans):
+        out, a = ref.scan(s[0])
+        exp_act.append(a)
+        exp_rows += [(cpi, 0, t["id"], t["range_q2"], t["doppler_q2"], t["vel_r"], t["vel_d"], t["quality"], t["status"]) for t in out]
+    assert act[:, 0].tolist() == exp_act
+    assert act[1, 0] >= 2 and act[2, 0] >= 2 and act[5, 0] >= 3                 # tb_tws_tracker.vhd:134-153
+    assert [tuple(int(v) for v in t) for t in trk] == exp_rows and len(exp_rows) > 0
+    # --- random scans, 2 channels, some with > 64 detections, two calls sharing the track files
+    rng = np.random.default_rng(12)
+    n_scan, n_ch = 10, 2
+    scans = []
+    for s in range(n_scan):
+        chans = []
+        for ch in range(n_ch):
+            n = int(rng.choice([0, 1, 3, 8, 70, 130]))
+            base = [(100 + 3 * s + 11 * k, 10 + k, 500 + k) for k in range(4)]       # slowly moving targets in range < 512, Doppler < 64
+            rnd = [(int(rng.integers(0, 1024)), int(rng.integers(0, 128)), int(rng.integers(1, 60000))) for _ in range(n)]
+            chans.append(sorted(set(base + rnd)))
+        scans.append(chans)
+    dets, counts = _dets_from_scans(scans)
+    with make_core(n_range=1024, n_doppler=128, n_channels=n_ch, max_cpis=n_scan, max_dets_per_cpi=512) as c:
+        c.tracker_reset()
+        half = n_scan // 2
+        cut = int(counts[:half].sum())
+        d1 = dets[:cut].copy()
+        d2 = dets[cut:].copy()
+        d2["cpi"] -= half
+        t1, nt1, a1 = c.track(d1, counts[:half])
+        t2, nt2, a2 = c.track(d2, counts[half:])
+    t2 = t2.copy()
+    t2["cpi"] += half
+    got = [tuple(int(v) for v in t) for t in np.concatenate([t1, t2])]
+    act = np.concatenate([a1, a2])
+    refs = [tk.TwsTracker() for _ in range(n_ch)]
+    exp_rows = []
+    for cpi, chans in enumerate(scans):
+        for ch, lst in enumerate(chans):
+            out, a = refs[ch].scan(lst)
+            assert act[cpi, ch] == a
+            exp_rows += [(cpi, ch, t["id"], t["range_q2"], t["doppler_q2"], t["vel_r"], t["vel_d"], t["quality"], t["status"]) for t in out]
+    assert got == exp_rows and len(exp_rows) > 10

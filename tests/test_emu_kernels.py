@@ -94,3 +94,7 @@ def test_fixed_stages(make_core):
 @pytest.mark.parametrize("seed", range(6))
 def test_cfar_random_config(make_core, seed):
     pc.case_cfar_random_config(make_core, 1000 + seed)
+
+
+def test_tracker(make_core):
+    pc.case_tracker(make_core)

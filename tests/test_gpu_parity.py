@@ -118,6 +118,25 @@ def test_cfar_random_config(make_core, seed):
     pc.case_cfar_random_config(make_core, seed)
 
 
+def test_tracker(make_core):
+    pc.case_tracker(make_core)
+
+
+def test_track_file_from_the_whole_path(make_core, tmp_path):
+    """Cubes -> RD map -> CFAR -> tracker on one GPU; the log files have the reference's formats."""
+    tg = [(100, 5, 6000.0), (300, 40, 4000.0)]
+    cubes = np.concatenate([st.synthetic_cube(1, 1, 128, 1024, seed=50 + i, sigma=10.0,
+                                              fixed_targets=[(r - 2 * i, d, a) for (r, d, a) in tg])[0] for i in range(6)])
+    with make_core(n_range=1024, n_doppler=128, max_cpis=6, max_dets_per_cpi=1 << 15) as c:
+        dets, n_dets = (x.copy() for x in c.process(cubes, want_map=False)[1:3])
+        c.tracker_reset()
+        trk, nt, act = c.track(dets, n_dets)
+    assert act.shape == (6, 1) and act[-1, 0] >= 1 and len(trk) >= 1
+    n = rdp.write_tracks(tmp_path / "tracks.txt", trk, act)
+    lines = open(tmp_path / "tracks.txt").read().split("\n")
+    assert n == len(trk) + 6 and sum(l.startswith("SCAN_END ACTIVE=") for l in lines) == 6
+
+
 def test_fixed_stages(make_core):
     pc.case_fixed_stages(make_core)
 

@@ -123,6 +123,102 @@ __global__ void __launch_bounds__(256) k_f16_mask(const uint32_t* __restrict__ t
     out[blockIdx.x * 256 + threadIdx.x] = s;
 }
 
+// DPX: max(min(cut + (-ref), 1), 0) per signed 16-bit half = [ref < cut] on bf16 bit patterns (order-preserving for
+// non-negative values); the 0/1 halves add up directly
+__global__ void __launch_bounds__(256) k_dpx(const uint32_t* __restrict__ t, int* out, uint32_t c) {
+    uint32_t v[NR], cut[NC / 2]; unsigned cnt[NC / 2];
+    for (int i = 0; i < NR; ++i) v[i] = t[i * 256 + threadIdx.x];
+    for (int j = 0; j < NC / 2; ++j) { cut[j] = c + 0x00010001u * j; cnt[j] = 0; }
+    for (int it = 0; it < ITERS; ++it) {
+        #pragma unroll
+        for (int i = 0; i < NR; i += 2)
+            #pragma unroll
+            for (int j = 0; j < NC / 2; ++j)
+                cnt[j] += __viaddmin_s16x2_relu(cut[j], v[i], 0x00010001u) + __viaddmin_s16x2_relu(cut[j], v[i + 1], 0x00010001u);
+        #pragma unroll
+        for (int j = 0; j < NC / 2; ++j) cut[j] += 0x00010001u;
+    }
+    int s = 0; for (int j = 0; j < NC / 2; ++j) s += cnt[j];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+// SIMD-in-a-word compare intrinsic
+__global__ void __launch_bounds__(256) k_vcmp(const uint32_t* __restrict__ t, int* out, uint32_t c) {
+    uint32_t v[NR], cut[NC / 2]; unsigned cnt[NC / 2];
+    for (int i = 0; i < NR; ++i) v[i] = t[i * 256 + threadIdx.x];
+    for (int j = 0; j < NC / 2; ++j) { cut[j] = c + 0x00010001u * j; cnt[j] = 0; }
+    for (int it = 0; it < ITERS; ++it) {
+        #pragma unroll
+        for (int i = 0; i < NR; i += 2)
+            #pragma unroll
+            for (int j = 0; j < NC / 2; ++j) cnt[j] -= __vcmpltu2(v[i], cut[j]) + __vcmpltu2(v[i + 1], cut[j]);
+        #pragma unroll
+        for (int j = 0; j < NC / 2; ++j) cut[j] += 0x00010001u;
+    }
+    int s = 0; for (int j = 0; j < NC / 2; ++j) s += cnt[j];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+// saturating SIMD subtract: min(max(cut - ref, 0), ...) needs a second op; measure vsubus2 + vminu2
+__global__ void __launch_bounds__(256) k_vsub(const uint32_t* __restrict__ t, int* out, uint32_t c) {
+    uint32_t v[NR], cut[NC / 2]; unsigned cnt[NC / 2];
+    for (int i = 0; i < NR; ++i) v[i] = t[i * 256 + threadIdx.x];
+    for (int j = 0; j < NC / 2; ++j) { cut[j] = c + 0x00010001u * j; cnt[j] = 0; }
+    for (int it = 0; it < ITERS; ++it) {
+        #pragma unroll
+        for (int i = 0; i < NR; ++i)
+            #pragma unroll
+            for (int j = 0; j < NC / 2; ++j) cnt[j] += __vminu2(__vsubus2(cut[j], v[i]), 0x00010001u);
+        #pragma unroll
+        for (int j = 0; j < NC / 2; ++j) cut[j] += 0x00010001u;
+    }
+    int s = 0; for (int j = 0; j < NC / 2; ++j) s += cnt[j];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
+// HSET2 masks accumulated on the FMA pipe (IMAD acc = m * -1 + acc) instead of IADD3 on the ALU pipe
+__global__ void __launch_bounds__(256) k_bf16_imad(const uint32_t* __restrict__ t, int* out, uint32_t c) {
+    uint32_t v[NR], cut[NC / 2]; int cnt[NC / 2];
+    for (int i = 0; i < NR; ++i) v[i] = t[i * 256 + threadIdx.x];
+    for (int j = 0; j < NC / 2; ++j) { cut[j] = c + 0x00010001u * j; cnt[j] = 0; }
+    int minus1 = -(int)(c >> 31) - 1 + (int)(threadIdx.x >> 10);      // -1, opaque to the compiler
+    for (int it = 0; it < ITERS; ++it) {
+        #pragma unroll
+        for (int i = 0; i < NR; ++i)
+            #pragma unroll
+            for (int j = 0; j < NC / 2; ++j) {
+                uint32_t m0;
+                asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(m0) : "r"(v[i]), "r"(cut[j]));
+                asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(cnt[j]) : "r"(m0), "r"(minus1));
+            }
+        #pragma unroll
+        for (int j = 0; j < NC / 2; ++j) cut[j] += 0x00010001u;
+    }
+    int s = 0; for (int j = 0; j < NC / 2; ++j) s += cnt[j];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
+// half of the references through HSET2 (fp16-class pipe), half through VIADDMNMX (integer pipe)
+__global__ void __launch_bounds__(256) k_mix(const uint32_t* __restrict__ t, int* out, uint32_t c) {
+    uint32_t v[NR], cut[NC / 2], ncut[NC / 2]; unsigned cnt[NC / 2], cge[NC / 2];
+    for (int i = 0; i < NR; ++i) v[i] = t[i * 256 + threadIdx.x];
+    for (int j = 0; j < NC / 2; ++j) { cut[j] = c + 0x00010001u * j; ncut[j] = 0x00010001u - cut[j]; cnt[j] = 0; cge[j] = 0; }
+    for (int it = 0; it < ITERS; ++it) {
+        #pragma unroll
+        for (int i = 0; i < NR; i += 4)
+            #pragma unroll
+            for (int j = 0; j < NC / 2; ++j) {
+                uint32_t m0, m1;
+                asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(m0) : "r"(v[i]), "r"(cut[j]));
+                asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(m1) : "r"(v[i + 1]), "r"(cut[j]));
+                cnt[j] -= m0 + m1;
+                cge[j] += __viaddmin_s16x2_relu(v[i + 2], ncut[j], 0x00010001u) + __viaddmin_s16x2_relu(v[i + 3], ncut[j], 0x00010001u);
+            }
+        #pragma unroll
+        for (int j = 0; j < NC / 2; ++j) { cut[j] += 0x00010001u; ncut[j] -= 0x00010001u; }
+    }
+    int s = 0; for (int j = 0; j < NC / 2; ++j) s += cnt[j] + cge[j];
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
 template <class K, class T, class A>
 void run(const char* name, K k, const T* d_t, int* d_out, A arg, double compares_per_thread) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -152,5 +248,10 @@ int main() {
     run("bf16x2 mask", k_bf16_mask, (const uint32_t*)d_t, d_out, 0x40404040u, packed);
     run("bf16x2 add", k_bf16_add, (const uint32_t*)d_t, d_out, 0x40404040u, packed);
     run("f16x2 mask", k_f16_mask, (const uint32_t*)d_t, d_out, 0x40404040u, packed);
+    run("dpx viaddmin", k_dpx, (const uint32_t*)d_t, d_out, 0x40404040u, packed);
+    run("bf16x2+imad", k_bf16_imad, (const uint32_t*)d_t, d_out, 0x40404040u, packed);
+    run("hset2+dpx mix", k_mix, (const uint32_t*)d_t, d_out, 0x40404040u, packed);
+    run("vcmpltu2", k_vcmp, (const uint32_t*)d_t, d_out, 0x40404040u, packed);
+    run("vsubus2+vminu2", k_vsub, (const uint32_t*)d_t, d_out, 0x40404040u, packed);
     return 0;
 }
