@@ -48,11 +48,22 @@ struct K1Raw<1> {
     static __device__ __forceinline__ float2 cvt(T w) { return w; }
 };
 
+// Distributed corner turn (BASELINE config 4): the chirps of a CPI are sharded over `world` GPUs, the range
+// lines of the range-major intermediate over the same GPUs.  K1 then stores each range line straight into the
+// memory of the GPU that owns it (peer pointers opened through CUDA IPC, stores travel over NVLink): the
+// all-to-all exchange is fused into the transposed store instead of being a separate collective + repack.
+struct K1Scatter {
+    float2* peer[16];          // x_rc of every rank: [map][rows_local][n_chirps_total]
+    int world, rank;
+    int rows_shift;            // rows_local = 1 << rows_shift range lines per rank
+    int n_chirps_total;        // world * local chirps
+};
+
 template <class Plan, int IN_FMT>
 __global__ void __launch_bounds__(K1Shape<Plan>::THREADS)
 k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
                 const float* __restrict__ window, const float2* __restrict__ twtab,
-                int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles) {
+                int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc) {
     constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
     constexpr int G = K1Shape<Plan>::G, THREADS = K1Shape<Plan>::THREADS, TCM = K1Shape<Plan>::TC_MAX;
     using P0 = typename Plan::P0;
@@ -121,7 +132,17 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
         __syncthreads();
         // range-major store: row k of the tile -> x_rc[map][k][c0 .. c0+tile_chirps)
         float2* dst = x_rc + map * (long long)N * n_chirps + c0;
-        if (tile_chirps == TCM && (TCM % 2) == 0 && (n_chirps % 2) == 0) {
+        if (sc.world > 1) {
+            // range line k belongs to rank k >> rows_shift; this rank's chirps sit at column rank * n_chirps
+            const int rows_local = 1 << sc.rows_shift;
+            const int total = N * tile_chirps;
+            for (int i = threadIdx.x; i < total; i += THREADS) {
+                const int k = i / tile_chirps, c = i % tile_chirps;
+                float2* base = sc.peer[k >> sc.rows_shift];
+                base[(map * rows_local + (k & (rows_local - 1))) * (long long)sc.n_chirps_total + sc.rank * n_chirps + c0 + c] =
+                    tile[k * tcp + c];
+            }
+        } else if (tile_chirps == TCM && (TCM % 2) == 0 && (n_chirps % 2) == 0) {
             // compile-time tile width: each thread moves two adjacent chirps of one range bin per step with one
             // 128-bit store (rows of the output are 16-byte aligned: c0, n_chirps even); pointers just advance
             constexpr int HALF = TCM / 2, KSTEP = THREADS / HALF;

@@ -36,7 +36,7 @@ struct K1Launcher {
     size_t (*smem)(int tile_chirps);
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(int grid, size_t smem, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
-                   const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles);
+                   const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc);
 };
 struct K2Launcher {
     int T, G;
@@ -81,9 +81,9 @@ struct K1Inst {
         return prepare_kernel(k1_range_kernel<Plan, FMT>, K1Shape<Plan>::THREADS, s, occ);
     }
     static void launch(int grid, size_t s, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
-                       const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles) {
+                       const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc) {
         RDP_LAUNCH((k1_range_kernel<Plan, FMT>), grid, K1Shape<Plan>::THREADS, s, st, cube, x_rc, win, tw,
-                   n_chirps, tile_chirps, tiles_per_map, total_tiles);
+                   n_chirps, tile_chirps, tiles_per_map, total_tiles, sc);
     }
     static K1Launcher get() {
         return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch};
@@ -235,6 +235,7 @@ struct rdp_handle {
     float2* x_rc = nullptr;        // [chunk][channel][range][chirp]
     float* map_scratch[2] = {nullptr, nullptr};
     void* in_stage[2] = {nullptr, nullptr};
+    size_t cfar_rows_cap = 0;      // range lines the bitmask / row-offset scratch can hold
     uint32_t* det_bits = nullptr;  // [chunk][channel][range][words_per_row] detection bitmask
     int* row_off = nullptr;        // [chunk][channel][range] record offset of each range line within its CPI
     int* counts = nullptr;         // [max_cpis]
@@ -327,8 +328,12 @@ int launch_check(rdp_handle* h, const char* what) {
 }
 
 // ---- the three stages on device buffers (n_cpi <= any; no chunking here) -------------------
-int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc) {
+int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1Scatter* scatter = nullptr) {
     const rdp_config& c = h->cfg;
+    K1Scatter sc;
+    std::memset(&sc, 0, sizeof(sc));
+    sc.world = 1;
+    if (scatter) sc = *scatter;
     const int tc = h->k1_tile_chirps;
     const int tiles_per_map = c.n_chirps / tc;
     const long long total = (long long)n_cpi * c.n_channels * tiles_per_map;
@@ -337,14 +342,14 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc) {
         return fail(h, RDP_E_CAPACITY, "range stage: too many chirps in one launch; lower chunk_cpis");
     int grid = (int)(total < h->k1_grid_cap ? total : h->k1_grid_cap);
     stage_begin(h, 0);
-    h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total);
+    h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total, sc);
     stage_end(h);
     return launch_check(h, "k1_range_kernel");
 }
 
-int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map) {
+int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, long long rows_override = -1) {
     const rdp_config& c = h->cfg;
-    const long long rows = (long long)n_cpi * c.n_channels * c.n_samples;
+    const long long rows = rows_override >= 0 ? rows_override : (long long)n_cpi * c.n_channels * c.n_samples;
     if (rows == 0) return RDP_OK;
     long long blocks = (rows + h->k2.G - 1) / h->k2.G;
     int grid = (int)(blocks < h->k2_grid_cap ? blocks : h->k2_grid_cap);
@@ -357,10 +362,26 @@ int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map) {
 // K3 + K4 on n_cpi <= chunk maps-worth of CPIs: bitmask, then ordered compaction into dets / counts / status
 // (all three already offset to this chunk); cpi_label is the CPI index written into the records.
 int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp_det* dets, int* counts,
-             uint32_t* status, int cpi_label, int int_mode = 0) {
-    const rdp_config& c = h->cfg;
+             uint32_t* status, int cpi_label, int int_mode = 0, int n_range_rows = 0) {
+    rdp_config c = h->cfg;                                 // by value: n_samples may be overridden (sharded maps)
     CfarArgs args = h->cfar;
     args.int_mode = int_mode;
+    if (n_range_rows > 0) {
+        c.n_samples = n_range_rows;
+        args.n_range = n_range_rows;
+        // bitmask / row-offset scratch was sized for the configured map height; grow it if this one is taller
+        const size_t need = (size_t)n_cpi * c.n_channels * n_range_rows;
+        if (need > h->cfar_rows_cap) {
+            if (h->det_bits) cudaFree(h->det_bits);
+            if (h->row_off) cudaFree(h->row_off);
+            h->det_bits = nullptr; h->row_off = nullptr;
+            int rc = dev_alloc(h, &h->det_bits, need * args.words_per_row);
+            if (rc) return rc;
+            rc = dev_alloc(h, &h->row_off, need);
+            if (rc) return rc;
+            h->cfar_rows_cap = need;
+        }
+    }
     const long long maps = (long long)n_cpi * c.n_channels;
     if (maps == 0) return RDP_OK;
     stage_begin(h, 2);
@@ -401,7 +422,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     int rc = launch_check(h, "k3_cfar_kernel");
     if (rc) return rc;
     stage_begin(h, 3);
-    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, 256, 0, h->cur, h->det_bits, h->row_off, counts, status, h->cfar);
+    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, 256, 0, h->cur, h->det_bits, h->row_off, counts, status, args);
     const long long total_rows = maps * c.n_samples;
     int lanes_per_row = 1;
     while (lanes_per_row < args.words_per_row && lanes_per_row < 32) lanes_per_row <<= 1;
@@ -638,6 +659,7 @@ int init_handle(rdp_handle* h) {
     if (rc) return rc;
     rc = dev_alloc(h, &h->row_off, (size_t)chunk * c.n_channels * c.n_samples);
     if (rc) return rc;
+    h->cfar_rows_cap = (size_t)chunk * c.n_channels * c.n_samples;
     rc = dev_alloc(h, &h->counts, (size_t)c.max_cpis);
     if (rc) return rc;
     rc = dev_alloc(h, &h->status, (size_t)c.max_cpis);
@@ -1015,6 +1037,106 @@ int rdp_track_device(rdp_handle* h, const rdp_det* dets, const int32_t* n_dets, 
     RDP_LAUNCH(k6_tracker_kernel, h->cfg.n_channels, 32, 0, h->stream, dets, n_dets, n_cpi, h->trk_args, h->trk_state, tracks,
                n_tracks, active, 0);
     return launch_check(h, "k6_tracker_kernel");
+}
+
+// ---- sharded large CPI (BASELINE config 4): peer-store corner turn + row-count overrides + CUDA IPC -------------
+int rdp_range_stage_scatter(rdp_handle* h, const void* cube, int32_t n_cpi, const rdp_scatter* sc) {
+    if (!h || !cube || !sc || n_cpi < 0 || sc->world < 1 || sc->world > 16 || sc->rank < 0 || sc->rank >= sc->world)
+        return fail(h, RDP_E_INVALID, "rdp_range_stage_scatter: bad argument");
+    const rdp_config& c = h->cfg;
+    if (c.n_samples % sc->world != 0 || !is_pow2(c.n_samples / sc->world))
+        return fail(h, RDP_E_INVALID, "n_samples / world must be a power of two");
+    K1Scatter k;
+    std::memset(&k, 0, sizeof(k));
+    for (int i = 0; i < sc->world; ++i) {
+        if (!sc->peer[i]) return fail(h, RDP_E_INVALID, "rdp_range_stage_scatter: peer[%d] is NULL", i);
+        k.peer[i] = reinterpret_cast<float2*>(sc->peer[i]);
+    }
+    k.world = sc->world;
+    k.rank = sc->rank;
+    k.rows_shift = 0;
+    while ((1 << k.rows_shift) < c.n_samples / sc->world) ++k.rows_shift;
+    k.n_chirps_total = c.n_chirps * sc->world;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    if (sc->world == 1) return run_range(h, cube, n_cpi, k.peer[0]);
+    return run_range(h, cube, n_cpi, k.peer[sc->rank], &k);
+}
+
+int rdp_doppler_stage_rows(rdp_handle* h, const void* x_rc, int64_t n_rows, float* rd_map) {
+    if (!h || !x_rc || !rd_map || n_rows < 0) return fail(h, RDP_E_INVALID, "rdp_doppler_stage_rows: bad argument");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    return run_doppler(h, reinterpret_cast<const float2*>(x_rc), 0, rd_map, n_rows);
+}
+
+int rdp_cfar_stage_rows(rdp_handle* h, const float* rd_map, int32_t n_cpi, int32_t n_range_rows, float* cfar_out,
+                        rdp_det* dets, int32_t* n_dets, uint32_t* status) {
+    if (!h || !rd_map || !dets || !n_dets || !status || n_cpi < 0 || n_range_rows < 1)
+        return fail(h, RDP_E_INVALID, "rdp_cfar_stage_rows: bad argument");
+    const rdp_config& c = h->cfg;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    const size_t cells = (size_t)c.n_channels * n_range_rows * c.n_chirps;
+    for (int base = 0; base < n_cpi; base += h->chunk) {
+        const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
+        int rc = run_cfar(h, rd_map + (size_t)base * cells, n, cfar_out ? cfar_out + (size_t)base * cells : nullptr,
+                          dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base, 0, n_range_rows);
+        if (rc) return rc;
+    }
+    return RDP_OK;
+}
+
+int rdp_ipc_export(rdp_handle* h, void* device_ptr, unsigned char handle_bytes[64]) {
+    if (!h || !device_ptr || !handle_bytes) return RDP_E_INVALID;
+#ifdef RDP_EMU
+    std::memset(handle_bytes, 0, 64);
+    std::memcpy(handle_bytes, &device_ptr, sizeof(void*));       // single-process emulation: the pointer itself
+    return RDP_OK;
+#else
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    RDP_CUDA(h, cudaIpcGetMemHandle(&mh, device_ptr));
+    std::memcpy(handle_bytes, &mh, 64);
+    return RDP_OK;
+#endif
+}
+
+int rdp_ipc_open(rdp_handle* h, const unsigned char handle_bytes[64], void** device_ptr) {
+    if (!h || !handle_bytes || !device_ptr) return RDP_E_INVALID;
+#ifdef RDP_EMU
+    std::memcpy(device_ptr, handle_bytes, sizeof(void*));
+    return RDP_OK;
+#else
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, handle_bytes, 64);
+    RDP_CUDA(h, cudaIpcOpenMemHandle(device_ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    return RDP_OK;
+#endif
+}
+
+int rdp_ipc_close(rdp_handle* h, void* device_ptr) {
+    if (!h || !device_ptr) return RDP_E_INVALID;
+#ifndef RDP_EMU
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaIpcCloseMemHandle(device_ptr));
+#endif
+    return RDP_OK;
+}
+
+int rdp_copy_d2d(rdp_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!h || (!dst && bytes) || (!src && bytes)) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RDP_OK;
+}
+
+int rdp_device_memset(rdp_handle* h, void* dst, int value, size_t bytes) {
+    if (!h || (!dst && bytes)) return RDP_E_INVALID;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaMemsetAsync(dst, value, bytes, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RDP_OK;
 }
 
 int rdp_stream_open(rdp_handle* h, int32_t n_slots, int32_t slot_cpis) {

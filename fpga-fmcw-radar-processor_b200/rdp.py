@@ -57,6 +57,10 @@ class RdpTrackerConfig(C.Structure):
                                          "alpha_gain", "beta_gain")]
 
 
+class RdpScatter(C.Structure):
+    _fields_ = [("peer", C.c_void_p * 16), ("world", C.c_int32), ("rank", C.c_int32)]
+
+
 class RdpInfo(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("sm_count", C.c_int32),
                 ("chunk_cpis", C.c_int32), ("cfar_tma", C.c_int32), ("reserved", C.c_int32), ("scratch_bytes", C.c_int64), ("kernel_launches", C.c_int64),
@@ -82,6 +86,14 @@ SYMBOLS = {
     "rdp_fixed_mti": (C.c_int, [_VP, _VP, C.c_int64, _I32, _I32, _VP]),
     "rdp_fixed_magnitude": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "rdp_fixed_corner_turn": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP]),
+    "rdp_range_stage_scatter": (C.c_int, [_VP, _VP, _I32, C.POINTER(RdpScatter)]),
+    "rdp_doppler_stage_rows": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
+    "rdp_cfar_stage_rows": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
+    "rdp_ipc_export": (C.c_int, [_VP, _VP, C.c_char_p]),
+    "rdp_ipc_open": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
+    "rdp_ipc_close": (C.c_int, [_VP, _VP]),
+    "rdp_copy_d2d": (C.c_int, [_VP, _VP, _VP, _SZ]),
+    "rdp_device_memset": (C.c_int, [_VP, _VP, C.c_int, _SZ]),
     "rdp_tracker_reset": (C.c_int, [_VP, C.POINTER(RdpTrackerConfig)]),
     "rdp_track_device": (C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
     "rdp_stream_open": (C.c_int, [_VP, _I32, _I32]),

@@ -122,6 +122,15 @@ typedef struct rdp_tracker_config {
     int32_t beta_gain;         /* BETA_GAIN (Q8)              default 64  */
 } rdp_tracker_config;
 
+/* Destination of the distributed corner turn (rdp_range_stage_scatter): the range-major intermediate of every
+ * rank, [map][n_samples / world][n_chirps * world] complex64, as device pointers valid in THIS process (the
+ * rank's own buffer and the peers' buffers opened with rdp_ipc_open).                                      */
+typedef struct rdp_scatter {
+    void*   peer[16];
+    int32_t world;
+    int32_t rank;
+} rdp_scatter;
+
 typedef struct rdp_info {
     int32_t abi_version;
     int32_t device;
@@ -234,6 +243,28 @@ int rdp_stream_close(rdp_handle* h);
 int rdp_tracker_reset(rdp_handle* h, const rdp_tracker_config* cfg);
 int rdp_track_device(rdp_handle* h, const rdp_det* dets, const int32_t* n_dets, int32_t n_cpi, rdp_track* tracks,
                      int32_t* n_tracks, int32_t* active);
+
+/* Sharded large CPI (BASELINE config 4: one CPI spread over the GPUs of a box).  Each rank holds n_chirps
+ * of the CPI's n_chirps * world chirps and owns n_samples / world of its range lines:
+ *   rdp_range_stage_scatter  window + range FFT of the local chirps, each range line stored DIRECTLY into the
+ *                            owning rank's intermediate (peer stores over NVLink: the all-to-all corner turn is
+ *                            fused into K1's transposed store, no separate collective or repack); the caller
+ *                            barriers across ranks before the Doppler stage reads
+ *   rdp_doppler_stage_rows   Doppler stage on an explicit number of range lines (handle: n_chirps = the full
+ *                            chirp count)
+ *   rdp_cfar_stage_rows      CFAR stage on maps of an explicit number of range lines (own lines + halo lines
+ *                            copied from the neighbouring ranks)
+ *   rdp_ipc_export / open / close   CUDA IPC handles (64 opaque bytes) to map a peer rank's buffer
+ *   rdp_copy_d2d, rdp_device_memset device-side copy (also from a mapped peer buffer) and fill            */
+int rdp_range_stage_scatter(rdp_handle* h, const void* cube, int32_t n_cpi, const rdp_scatter* sc);
+int rdp_doppler_stage_rows(rdp_handle* h, const void* x_rc, int64_t n_rows, float* rd_map);
+int rdp_cfar_stage_rows(rdp_handle* h, const float* rd_map, int32_t n_cpi, int32_t n_range_rows, float* cfar_out,
+                        rdp_det* dets, int32_t* n_dets, uint32_t* status);
+int rdp_ipc_export(rdp_handle* h, void* device_ptr, unsigned char handle_bytes[64]);
+int rdp_ipc_open(rdp_handle* h, const unsigned char handle_bytes[64], void** device_ptr);
+int rdp_ipc_close(rdp_handle* h, void* device_ptr);
+int rdp_copy_d2d(rdp_handle* h, void* dst_device, const void* src_device, size_t bytes);
+int rdp_device_memset(rdp_handle* h, void* dst_device, int value, size_t bytes);
 
 /* Device / pinned-host memory owned by the caller (so a ctypes host needs no other CUDA binding). */
 int rdp_device_alloc(rdp_handle* h, size_t bytes, void** ptr);

@@ -98,3 +98,15 @@ def test_cfar_random_config(make_core, seed):
 
 def test_tracker(make_core):
     pc.case_tracker(make_core)
+
+
+@pytest.fixture(scope="module")
+def make_sharded(make_core):
+    def factory(**kw):
+        return rdp.ShardedCpi(library=EMU, _test_allow_emulator=True, **kw)
+    return factory
+
+
+@pytest.mark.parametrize("world,kw", [(4, dict()), (2, dict(cfar_axes="as_named", mti_mode=2, input_format="int16"))])
+def test_sharded_cpi(make_sharded, make_core, world, kw):
+    pc.case_sharded_cpi(make_sharded, make_core, world=world, **kw)

@@ -215,6 +215,38 @@ def test_streaming(make_core):
     pc.case_streaming(make_core, 512, 256, n_sub=5, n_slots=2)
 
 
+def test_sharded_cpi_one_process(make_core):
+    """Config 4 in miniature on one GPU: the ranks of the sharded mode simulated in lockstep in one process."""
+    def make_sharded(**kw):
+        return rdp.ShardedCpi(**kw)
+    pc.case_sharded_cpi(make_sharded, make_core, world=4)
+    pc.case_sharded_cpi(make_sharded, make_core, world=8, n_chirps=256, n_samples=1024, n_ch=1, n_cpi=1,
+                        cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2)
+
+
+def test_sharded_cpi_multi_gpu():
+    """The real thing: one process per GPU, K1 storing into peer memory over NVLink (needs >= 2 GPUs)."""
+    import subprocess
+    import sys
+    import ctypes
+    try:
+        cuda = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        cuda.cuInit(0)
+        cuda.cuDeviceGetCount(ctypes.byref(n))
+    except OSError:
+        pytest.skip("no CUDA driver")
+    if n.value < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n.value < 4 else (4 if n.value < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577",
+                          os.path.join(root, "tests", "dist_sharded_worker.py"), "1024", "4096"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 # ---- full-size, size-independent properties ---------------------------------------------------------
 def test_full_size_properties(make_core):
     """BASELINE config-3 shape (256 x 512 x 12 channels), 4 CPIs: determinism, exact x2 scaling
