@@ -15,6 +15,7 @@ mode exists for a CPI too large for one GPU's memory, and is exercised at small 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -80,13 +81,18 @@ class ShardedCpi:
             hb = C.create_string_buffer(64)
             self.core_b._check(lib.rdp_ipc_export(h, buf.ptr, hb))
             out.append(hb.raw)
-        return tuple(out)
+        # an IPC handle cannot be opened by the process that exported it: ranks simulated inside one process
+        # (tests) use the raw pointers instead
+        return (os.getpid(), self.d_xrc.ptr.value, self.d_map.ptr.value) + tuple(out)
 
     def connect(self, handles_of_all_ranks):
         lib, h = self.core_b.lib, self.core_b.h
-        for r, (hx, hm) in enumerate(handles_of_all_ranks):
+        for r, (pid, px, pm, hx, hm) in enumerate(handles_of_all_ranks):
             if r == self.rank:
                 self.peer_xrc[r], self.peer_map[r] = self.d_xrc.ptr.value, self.d_map.ptr.value
+                continue
+            if pid == os.getpid():
+                self.peer_xrc[r], self.peer_map[r] = px, pm
                 continue
             ptrs = []
             for raw in (hx, hm):
@@ -159,10 +165,8 @@ class ShardedCpi:
     def run(self, cube_local: np.ndarray, exchange):
         """cube_local: this rank's chirps [cpi, channel, n_chirps / world, sample(, 2)].  Returns (this rank's
         detections with global range indices, its lines of the RD map)."""
-        if not self._opened and self.world > 1:
-            self.connect(exchange.all_gather(self.export_handles()))
-        elif self.world == 1:
-            self.connect([self.export_handles()])
+        if self.peer_xrc[self.rank] is None:
+            self.connect(exchange.all_gather(self.export_handles()) if self.world > 1 else [self.export_handles()])
         exchange.barrier()
         self.range_scatter(cube_local)
         exchange.barrier()                                           # every rank's lines are complete
