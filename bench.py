@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="CPIs per internal pass (0 = auto, L2-sized)")
     ap.add_argument("--e2e-cpis", type=int, default=256)
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic CPIs tiled over the batch")
-    ap.add_argument("--max-dets", type=int, default=32768, help="detection-list capacity per CPI")
+    ap.add_argument("--max-dets", type=int, default=131072, help="detection-list capacity per CPI")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
@@ -354,7 +354,8 @@ def main():
                            "device": info["device_name"], "cfar_tile_staging": "TMA" if core.info()["cfar_tma"] else "manual", "sharding": "CPIs dealt to ranks, no data-path collective"},
                 "clocks": clocks, "e2e": e2e, "streaming": streaming, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu,
-                "detections_per_cpi_mean": float(counts.mean()), "status_or": int(np.bitwise_or.reduce(status))}
+                "detections_per_cpi_mean": float(counts.mean()), "detections_per_cpi_max": int(counts.max()),
+                "max_dets_per_cpi": int(core.max_dets_per_cpi), "status_or": int(np.bitwise_or.reduce(status))}
         print(json.dumps(line), flush=True)
     core.close()
     if dist is not None:

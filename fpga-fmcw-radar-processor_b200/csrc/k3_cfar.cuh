@@ -17,6 +17,15 @@
 // IADD3): measured 3.5x the rate of FSETP + predicated add on B200
 // (profiles/r1_mb_cmpacc_b200.txt).  ref_lo <= fl(v*s1) < cut <= cut_hi, so the packed count never
 // undercounts: no true detection is rejected.
+// In adaptive mode the pre-filter threshold is tightened per cell before it is rounded up: a cell can only
+// be detected with the scale the RTL would pick, so
+//     detection  =>  x_k < T = max(cut / SCALE_MAX, cut / SCALE_NOM, min(cut / SCALE_MIN, lo'))
+// where lo' >= lo = mean / 2 is an upper bound of the reference mean (the sum over the whole window, columns
+// widened to aligned groups of four, from a separable box filter over the staged tile).  SCALE_MIN is only
+// chosen when x_k < lo (:197), i.e. next to strong cells, so ordinary noise cells are tested against
+// cut / SCALE_NOM instead of cut / SCALE_MIN and almost never reach phase 2 (bench maps: survivors 5.0 % ->
+// 2.1 % of cells with 1.75 % true detections).  All bounds carry a 1e-3 relative margin, far above float32
+// rounding and far below the bfloat16 step; the decision itself stays with the exact phase 2.
 // Phase 2 (survivors only, ~0.5 % of noise cells + target cells): one warp per survivor decides
 // EXACTLY in float32 from the raw tile -- the s1 test, then (adaptive mode) float64 sum -> mean
 // -> scale 2/4/6 (:189-199) -> final test.  Decisions set bits in a per-tile bitmask.
@@ -41,6 +50,9 @@ struct CfarArgs {
     int int_mode;                           // 1: the map holds unsigned integers and the decision is the bit-exact
                                             //    integer arithmetic of os_cfar_2d.vhd (DATA_WIDTH = 17)
     int is1, ismin, isnom, ismax;           // the scales as integers (int_mode)
+    // pre-filter threshold in the s1-scaled domain: Ts = max(cut * pf_a, min(cut * pf_b, window_sum * pf_c))
+    // (non-adaptive: pf_a = 1, pf_b = 0, i.e. Ts = cut)
+    float pf_a, pf_b, pf_c;
 };
 
 // magnitude word -> float for the pre-filter; integers below 2^24 convert exactly
@@ -158,9 +170,14 @@ struct K3Shape {
     static constexpr int TF_WORDS = (SROWS * SCOLS + 4 + 31) / 32 * 32;   // one raw stage (+ a cell that reads 0.0f), 128 B multiple
     static constexpr int ZERO_IDX = SROWS * SCOLS;
     static constexpr int TILE_BYTES = SROWS * SCOLS * 4;
+    // window-sum bound of the adaptive pre-filter: column groups of 4, NCOV groups cover any window
+    static constexpr int NCG = SCOLS / 4, NCOV = (2 * HC + 7) / 4;
+    static constexpr int SURV_WORDS = TROWS * TCOLS / 2;
+    static_assert(TROWS * TCOLS <= 65536, "survivor codes are 16-bit");
+    static_assert(4 * NCOV >= 2 * HC + 1 + 3, "NCOV groups cover the window at any alignment");
     static constexpr size_t smem_bytes() {
         return sizeof(float) * (2 * TF_WORDS + SROWS * SCOLS) +
-               sizeof(int) * (TROWS * TCOLS + TROWS * TWORDS + 4 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
+               sizeof(int) * (SURV_WORDS + SROWS * NCG + TROWS * TWORDS + 4 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
     }
 };
 
@@ -234,12 +251,13 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     static_assert(S == 8, "the strip is four packed pairs");
     using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
     RDP_DYN_SMEM(smem_raw);
-    // 128-byte aligned carve-up: [2 raw stages][packed tile][survivors][bitmask][counter][window table][mbarriers]
+    // 128-byte aligned carve-up: [2 raw stages][packed tile][survivors][group sums][bitmask][counter][window table][mbarriers]
     unsigned char* smem_al = smem_raw + ((128 - ((uintptr_t)smem_raw & 127)) & 127);
     float* tf0 = reinterpret_cast<float*>(smem_al);                            // raw magnitudes, two stages
     uint32_t* th = reinterpret_cast<uint32_t*>(tf0 + 2 * Sh::TF_WORDS);        // bf16x2 (lo, lo) of fl(v*s1)
-    int* surv = reinterpret_cast<int*>(th + Sh::SROWS * Sh::SCOLS);
-    uint32_t* bits = reinterpret_cast<uint32_t*>(surv + Sh::TROWS * TCOLS);
+    unsigned short* surv = reinterpret_cast<unsigned short*>(th + Sh::SROWS * Sh::SCOLS);   // 16-bit survivor codes
+    float* grp = reinterpret_cast<float*>(surv) + Sh::SURV_WORDS;              // [SROWS][NCG] sums of 4 NCOV columns
+    uint32_t* bits = reinterpret_cast<uint32_t*>(grp + Sh::SROWS * Sh::NCG);
     int* n_surv = reinterpret_cast<int*>(bits + Sh::TROWS * Sh::TWORDS);
     int* wtab = n_surv + 4;                                                    // [NSLOT][2]: tf index = ctr * mul + add
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wtab + 2 * Sh::NSLOT);
@@ -297,14 +315,46 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         // int_mode: the product is rounded toward zero so that ref_lo never exceeds the exact integer product
         const float4* tf4 = reinterpret_cast<const float4*>(tf);
         uint4* th4 = reinterpret_cast<uint4*>(th);
-        for (int i = threadIdx.x; i < Sh::SROWS * Sh::SCOLS / 4; i += 256) {
-            const float4 r = tf4[i];
-            uint4 o;
-            o.x = bf16_dup(cfar_scaled(r.x, a.s1, INT_MODE));
-            o.y = bf16_dup(cfar_scaled(r.y, a.s1, INT_MODE));
-            o.z = bf16_dup(cfar_scaled(r.z, a.s1, INT_MODE));
-            o.w = bf16_dup(cfar_scaled(r.w, a.s1, INT_MODE));
-            th4[i] = o;
+        if (a.adaptive) {
+            // ... and, for the adaptive pre-filter bound, grp[row][g] = sum of the 4 NCOV columns from group g on
+            // (each warp steps by 32 - (NCOV - 1) chunks so that the neighbours it needs sit in its own lanes)
+            constexpr int OV = Sh::NCOV - 1, ADV = 32 - OV, NCH = Sh::SROWS * Sh::SCOLS / 4;
+            const int lane_s = threadIdx.x % 32;
+            for (int base = (threadIdx.x / 32) * ADV; base < NCH; base += 8 * ADV) {
+                const int i = base + lane_s;
+                float g = 0.0f;
+                if (i < NCH) {
+                    const float4 r = tf4[i];
+                    if (lane_s < ADV) {
+                        uint4 o;
+                        o.x = bf16_dup(cfar_scaled(r.x, a.s1, INT_MODE));
+                        o.y = bf16_dup(cfar_scaled(r.y, a.s1, INT_MODE));
+                        o.z = bf16_dup(cfar_scaled(r.z, a.s1, INT_MODE));
+                        o.w = bf16_dup(cfar_scaled(r.w, a.s1, INT_MODE));
+                        th4[i] = o;
+                    }
+                    g = (cfar_as_float(r.x, INT_MODE) + cfar_as_float(r.y, INT_MODE)) +
+                        (cfar_as_float(r.z, INT_MODE) + cfar_as_float(r.w, INT_MODE));
+                }
+                float cover = g;
+                const int cg = i % Sh::NCG;                       // groups past the end of the row count as 0
+                RDP_UNROLL
+                for (int k = 1; k <= OV; ++k) {
+                    const float nb = __shfl_down_sync(0xffffffffu, g, k);
+                    cover += cg + k < Sh::NCG ? nb : 0.0f;
+                }
+                if (lane_s < ADV && i < NCH) grp[i] = cover;
+            }
+        } else {
+            for (int i = threadIdx.x; i < Sh::SROWS * Sh::SCOLS / 4; i += 256) {
+                const float4 r = tf4[i];
+                uint4 o;
+                o.x = bf16_dup(cfar_scaled(r.x, a.s1, INT_MODE));
+                o.y = bf16_dup(cfar_scaled(r.y, a.s1, INT_MODE));
+                o.z = bf16_dup(cfar_scaled(r.z, a.s1, INT_MODE));
+                o.w = bf16_dup(cfar_scaled(r.w, a.s1, INT_MODE));
+                th4[i] = o;
+            }
         }
     } else
 #endif
@@ -331,6 +381,16 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                 }
             }
         }
+        if (a.adaptive) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < Sh::SROWS * Sh::NCG; i += 256) {
+                float cover = 0.0f;
+                RDP_UNROLL
+                for (int k = 0; k < 4 * Sh::NCOV; ++k)
+                    if (4 * (i % Sh::NCG) + k < Sh::SCOLS) cover += cfar_as_float(tf[4 * i + k], INT_MODE);
+                grp[i] = cover;
+            }
+        }
     }
     __syncthreads();
 
@@ -339,18 +399,50 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     const int col = c0 + tx;
     uint32_t cb[4], cl[4], ch[4], acc[4];
     bool force[S];
+    float wsum[S];                                                // adaptive: bound of the window sum of each cell
+    if (a.adaptive) {
+        // vertical pass of the box filter in registers: wsum[j] = sum_{k = j .. j + 2 HL} x[k], additions only
+        const float* gp = grp + (ty * S) * Sh::NCG + ((tx + Sh::HCP - HC) >> 2);
+        float x[S + 2 * HL];
+        RDP_UNROLL
+        for (int k = 0; k < S + 2 * HL; ++k) x[k] = gp[k * Sh::NCG];
+        if constexpr (2 * HL >= S - 1) {
+            float common = x[S - 1];                              // lines S-1 .. 2 HL belong to every window
+            RDP_UNROLL
+            for (int k = S; k <= 2 * HL; ++k) common += x[k];
+            float part = 0.0f;
+            wsum[S - 1] = common;
+            RDP_UNROLL
+            for (int j = S - 2; j >= 0; --j) { part += x[j]; wsum[j] = common + part; }
+            part = 0.0f;
+            RDP_UNROLL
+            for (int j = 1; j < S; ++j) { part += x[2 * HL + j]; wsum[j] += part; }
+        } else {
+            RDP_UNROLL
+            for (int j = 0; j < S; ++j) {
+                wsum[j] = 0.0f;
+                RDP_UNROLL
+                for (int k = 0; k <= 2 * HL; ++k) wsum[j] += x[j + k];
+            }
+        }
+    }
     RDP_UNROLL
     for (int p = 0; p < 4; ++p) {
-        const float c_lo = cfar_as_float(tf[(ty * S + 2 * p + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
-        const float c_hi = cfar_as_float(tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
+        const float cut_lo = cfar_as_float(tf[(ty * S + 2 * p + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
+        const float cut_hi = cfar_as_float(tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
+        float c_lo = cut_lo, c_hi = cut_hi;
+        if (a.adaptive) {
+            c_lo = fmaxf(c_lo * a.pf_a, fminf(c_lo * a.pf_b, wsum[2 * p] * a.pf_c));
+            c_hi = fmaxf(c_hi * a.pf_a, fminf(c_hi * a.pf_b, wsum[2 * p + 1] * a.pf_c));
+        }
         const uint32_t h0 = bf16_up(c_lo), h1 = bf16_up(c_hi);
         cb[p] = h0 | (h1 << 16);
         cl[p] = h0;
         ch[p] = h1 << 16;
         acc[p] = 0u;
         // bfloat16 subnormal range: leave the decision to the exact phase
-        force[2 * p] = c_lo > 0.0f && c_lo < 1e-36f;
-        force[2 * p + 1] = c_hi > 0.0f && c_hi < 1e-36f;
+        force[2 * p] = cut_lo > 0.0f && c_lo < 1e-36f;
+        force[2 * p + 1] = cut_hi > 0.0f && c_hi < 1e-36f;
     }
     const uint32_t* tp = th + (ty * S) * Sh::SCOLS + tx + Sh::HCP;
     for (int dc = -HC; dc <= HC; ++dc) {
@@ -364,7 +456,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             const uint32_t lo16 = acc[j >> 1] & 0xffffu;
             const uint32_t cnt = (j & 1) ? (((acc[j >> 1] >> 16) + lo16) & 0xffffu) : lo16;
             if (cfar_out) cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)line * a.n_doppler + col] = 0.0f;
-            if ((int)cnt >= a.rank_idx + 1 || force[j]) surv[atomicAdd(n_surv, 1)] = ((ty * S + j) << 16) | tx;
+            if ((int)cnt >= a.rank_idx + 1 || force[j]) surv[atomicAdd(n_surv, 1)] = (unsigned short)((ty * S + j) * TCOLS + tx);
         }
     }
     __syncthreads();
@@ -381,8 +473,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     for (int i0 = warp * (32 / G); i0 < ns; i0 += 8 * (32 / G)) {
         const int i = i0 + grp;
         const bool valid = i < ns;
-        const int code = valid ? surv[i] : 0;                      // idle groups chew on tile cell (0, 0)
-        const int tl = code >> 16, tcx = code & 0xffff;
+        const int code = valid ? (int)surv[i] : 0;                 // idle groups chew on tile cell (0, 0)
+        const int tl = code / TCOLS, tcx = code % TCOLS;
         const int cidx = (tl + HL) * Sh::SCOLS + tcx + Sh::HCP;
         bool det;
         if (!INT_MODE) {

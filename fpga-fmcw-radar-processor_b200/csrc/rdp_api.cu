@@ -606,6 +606,15 @@ int init_handle(rdp_handle* h) {
     } else {
         a.s1 = (float)c.scale_override;
     }
+    if (a.adaptive) {
+        // detection => x_k < max(cut / smax, cut / snom, min(cut / smin, mean / 2)); times s1, with a 1e-3 margin
+        const float big = a.snom < a.smax ? a.snom : a.smax;
+        a.pf_a = a.s1 / big * 1.001f;
+        a.pf_b = a.s1 / a.smin * 1.001f;
+        a.pf_c = 0.5f * a.s1 / (float)a.n_ref * 1.002f;
+    } else {
+        a.pf_a = 1.0f; a.pf_b = 0.0f; a.pf_c = 0.0f;
+    }
     a.raster = c.cfar_edges == RDP_EDGES_RASTER;
     a.int_mode = 0;
     a.is1 = (int)a.s1; a.ismin = c.scale_min; a.isnom = c.scale_nom; a.ismax = c.scale_max;
