@@ -445,9 +445,32 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         force[2 * p + 1] = cut_hi > 0.0f && c_hi < 1e-36f;
     }
     const uint32_t* tp = th + (ty * S) * Sh::SCOLS + tx + Sh::HCP;
-    for (int dc = -HC; dc <= HC; ++dc) {
-        if (dc >= -GC && dc <= GC) K3Rows<HL, GL, true, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
+    for (int dc = -HC; dc <= 0; ++dc) {
+        if (dc >= -GC) K3Rows<HL, GL, true, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
         else K3Rows<HL, GL, false, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
+    }
+    // Half-way exit: a cell needs rank_idx + 1 of its n_ref references below the threshold, so of the HALF_REFS
+    // references in columns -HC .. 0 at least HALF_REFS - (n_ref - rank_idx - 1) must be.  If no cell of the warp's
+    // 32 x S block gets there (noise-only blocks: almost never), the remaining columns cannot change any decision.
+    bool go_on = true;
+    {
+        constexpr int HALF_REFS = (HC - GC) * (2 * HL + 1) + (GC + 1) * (2 * HL - 2 * GL);
+        const int need = HALF_REFS - (a.n_ref - a.rank_idx - 1);
+        if (need > 0) {
+            bool mine = false;
+            RDP_UNROLL
+            for (int p = 0; p < 4; ++p) {
+                const uint32_t lo16 = acc[p] & 0xffffu, hi16 = ((acc[p] >> 16) + lo16) & 0xffffu;
+                mine = mine || (int)lo16 >= need || (int)hi16 >= need || force[2 * p] || force[2 * p + 1];
+            }
+            go_on = __any_sync(0xffffffffu, mine);
+        }
+    }
+    if (go_on) {
+        for (int dc = 1; dc <= HC; ++dc) {
+            if (dc <= GC) K3Rows<HL, GL, true, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
+            else K3Rows<HL, GL, false, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
+        }
     }
     RDP_UNROLL
     for (int j = 0; j < S; ++j) {
