@@ -135,12 +135,24 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
         if (sc.world > 1) {
             // range line k belongs to rank k >> rows_shift; this rank's chirps sit at column rank * n_chirps
             const int rows_local = 1 << sc.rows_shift;
-            const int total = N * tile_chirps;
-            for (int i = threadIdx.x; i < total; i += THREADS) {
-                const int k = i / tile_chirps, c = i % tile_chirps;
-                float2* base = sc.peer[k >> sc.rows_shift];
-                base[(map * rows_local + (k & (rows_local - 1))) * (long long)sc.n_chirps_total + sc.rank * n_chirps + c0 + c] =
-                    tile[k * tcp + c];
+            const long long col0 = (long long)sc.rank * n_chirps + c0;
+            if (tile_chirps == TCM && (TCM % 2) == 0 && (n_chirps % 2) == 0) {
+                // two adjacent chirps per 128-bit store, as in the local path
+                constexpr int HALF = TCM / 2, KSTEP = THREADS / HALF;
+                const int c = (threadIdx.x % HALF) * 2;
+                for (int k = threadIdx.x / HALF; k < N; k += KSTEP) {
+                    float2* row = sc.peer[k >> sc.rows_shift] +
+                                  (map * rows_local + (k & (rows_local - 1))) * (long long)sc.n_chirps_total + col0 + c;
+                    const float2 a = tile[k * (TCM + 1) + c], b2 = tile[k * (TCM + 1) + c + 1];
+                    *reinterpret_cast<float4*>(row) = make_float4(a.x, a.y, b2.x, b2.y);
+                }
+            } else {
+                const int total = N * tile_chirps;
+                for (int i = threadIdx.x; i < total; i += THREADS) {
+                    const int k = i / tile_chirps, c = i % tile_chirps;
+                    float2* base = sc.peer[k >> sc.rows_shift];
+                    base[(map * rows_local + (k & (rows_local - 1))) * (long long)sc.n_chirps_total + col0 + c] = tile[k * tcp + c];
+                }
             }
         } else if (tile_chirps == TCM && (TCM % 2) == 0 && (n_chirps % 2) == 0) {
             // compile-time tile width: each thread moves two adjacent chirps of one range bin per step with one

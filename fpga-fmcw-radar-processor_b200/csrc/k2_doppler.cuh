@@ -3,7 +3,8 @@
 // Replaces doppler_notch -> window_multiplier (N_SAMPLES = N_DOPPLER) -> xfft_doppler ->
 // magnitude_calc of rtl/src/radar_core.vhd:329-374.  One FFT group per range line of the
 // range-major intermediate; the magnitude is formed in registers and written as float32
-// [range][doppler] (Doppler bin 0 = zero Doppler, natural order).
+// [range][doppler] (Doppler bin 0 = zero Doppler, natural order).  rows_per_map > 0 leaves pad_rows lines
+// free around every rows_per_map output lines (the CFAR halo of the range-sharded mode).
 //   algorithmic HBM bytes / cell: 8 read + 4 written.
 #pragma once
 #include "fft_core.cuh"
@@ -36,7 +37,7 @@ template <class Plan, int MAG>
 __global__ void __launch_bounds__(K2Shape<Plan>::THREADS)
 k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                   const float* __restrict__ window, const float2* __restrict__ twtab,
-                  long long n_rows, int mti_mode) {
+                  long long n_rows, int mti_mode, int rows_per_map, int pad_rows) {
     constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
     constexpr int G = K2Shape<Plan>::G;
     using P0 = typename Plan::P0;
@@ -100,7 +101,9 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
         fetch(row + stride);
         Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
         if (active) {
-            float* dst = rd_map + row * N;
+            // sharded mode: every map of rows_per_map lines is written with pad_rows halo lines above and below
+            const long long orow = rows_per_map > 0 ? row + (2 * (row / rows_per_map) + 1) * pad_rows : row;
+            float* dst = rd_map + orow * N;
             RDP_UNROLL
             for (int b = 0; b < PL::NB; ++b) {
                 RDP_UNROLL

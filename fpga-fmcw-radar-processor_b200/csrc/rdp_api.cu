@@ -43,7 +43,7 @@ struct K2Launcher {
     size_t smem;
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(int grid, size_t smem, cudaStream_t st, const float2* x_rc, float* rd_map, const float* win,
-                   const float2* tw, long long n_rows, int mti_mode);
+                   const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows);
 };
 struct K3Launcher {
     int trows, tcols;            // 0,0 => generic kernel
@@ -96,9 +96,9 @@ struct K2Inst {
         return prepare_kernel(k2_doppler_kernel<Plan, MAG>, K2Shape<Plan>::THREADS, s, occ);
     }
     static void launch(int grid, size_t s, cudaStream_t st, const float2* x_rc, float* rd_map, const float* win,
-                       const float2* tw, long long n_rows, int mti_mode) {
+                       const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows) {
         RDP_LAUNCH((k2_doppler_kernel<Plan, MAG>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
-                   n_rows, mti_mode);
+                   n_rows, mti_mode, rows_per_map, pad_rows);
     }
     static K2Launcher get() {
         return K2Launcher{Plan::T, K2Shape<Plan>::G, K2Shape<Plan>::smem_bytes(), &prepare, &launch};
@@ -347,14 +347,15 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1
     return launch_check(h, "k1_range_kernel");
 }
 
-int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, long long rows_override = -1) {
+int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, long long rows_override = -1,
+                int rows_per_map = 0, int pad_rows = 0) {
     const rdp_config& c = h->cfg;
     const long long rows = rows_override >= 0 ? rows_override : (long long)n_cpi * c.n_channels * c.n_samples;
     if (rows == 0) return RDP_OK;
     long long blocks = (rows + h->k2.G - 1) / h->k2.G;
     int grid = (int)(blocks < h->k2_grid_cap ? blocks : h->k2_grid_cap);
     stage_begin(h, 1);
-    h->k2.launch(grid, h->k2.smem, h->cur, x_rc, rd_map, h->win_d, h->tw_d, rows, c.mti_mode);
+    h->k2.launch(grid, h->k2.smem, h->cur, x_rc, rd_map, h->win_d, h->tw_d, rows, c.mti_mode, rows_per_map, pad_rows);
     stage_end(h);
     return launch_check(h, "k2_doppler_kernel");
 }
@@ -687,7 +688,7 @@ int ensure_host_path(rdp_handle* h) {
     }
     int rc = dev_alloc(h, &h->dets, (size_t)c.max_cpis * c.max_dets_per_cpi);
     if (rc) return rc;
-    rc = dev_alloc(h, &h->packed, (size_t)c.max_cpis * c.max_dets_per_cpi);
+    if (!h->packed) rc = dev_alloc(h, &h->packed, (size_t)c.max_cpis * c.max_dets_per_cpi);
     if (rc) return rc;
     for (int i = 0; i < 2; ++i) {
         cudaEvent_t e;
@@ -939,6 +940,36 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
     return RDP_OK;
 }
 
+// Device detection rows [n_cpi][max_dets_per_cpi] + counts -> one packed host list (pack kernel + a single D2H copy).
+int rdp_gather_dets(rdp_handle* h, const rdp_det* dets, const int32_t* n_dets, int32_t n_cpi, rdp_det* dets_host,
+                    int32_t* counts_host, int64_t* total_out) {
+    if (!h || !dets || !n_dets || !dets_host || !counts_host || !total_out || n_cpi < 0)
+        return fail(h, RDP_E_INVALID, "rdp_gather_dets: bad argument");
+    const rdp_config& c = h->cfg;
+    if (n_cpi > c.max_cpis) return fail(h, RDP_E_CAPACITY, "rdp_gather_dets: %d CPIs exceed max_cpis = %d", n_cpi, c.max_cpis);
+    *total_out = 0;
+    if (n_cpi == 0) return RDP_OK;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    h->launches += 1;
+    if (!h->packed) {                                             // scratch of the host path, allocated on first use
+        int rc0 = dev_alloc(h, &h->packed, (size_t)c.max_cpis * c.max_dets_per_cpi);
+        if (rc0) return rc0;
+    }
+    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, dets, n_dets, h->packed, c.max_dets_per_cpi, 0);
+    int rc = launch_check(h, "k5_pack_dets_kernel");
+    if (rc) return rc;
+    RDP_CUDA(h, cudaMemcpyAsync(counts_host, n_dets, sizeof(int) * (size_t)n_cpi, cudaMemcpyDeviceToHost, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    long long total = 0;
+    for (int i = 0; i < n_cpi; ++i) total += counts_host[i] < c.max_dets_per_cpi ? counts_host[i] : c.max_dets_per_cpi;
+    if (total > 0) {
+        RDP_CUDA(h, cudaMemcpyAsync(dets_host, h->packed, sizeof(rdp_det) * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+        RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    *total_out = total;
+    return RDP_OK;
+}
+
 // ---- 16-bit fixed-point stage taps (bit-exact restatements of the hand-written RTL stages) ------------
 int rdp_fixed_window(rdp_handle* h, const void* in, int64_t n_rows, int32_t n, void* out, uint32_t* saturated) {
     if (!h || !in || !out || n_rows < 0 || n < 2 || (n & 1)) return fail(h, RDP_E_INVALID, "rdp_fixed_window: bad argument");
@@ -1071,10 +1102,12 @@ int rdp_range_stage_scatter(rdp_handle* h, const void* cube, int32_t n_cpi, cons
     return run_range(h, cube, n_cpi, k.peer[sc->rank], &k);
 }
 
-int rdp_doppler_stage_rows(rdp_handle* h, const void* x_rc, int64_t n_rows, float* rd_map) {
-    if (!h || !x_rc || !rd_map || n_rows < 0) return fail(h, RDP_E_INVALID, "rdp_doppler_stage_rows: bad argument");
+int rdp_doppler_stage_rows(rdp_handle* h, const void* x_rc, int64_t n_rows, int32_t rows_per_map, int32_t pad_rows,
+                           float* rd_map) {
+    if (!h || !x_rc || !rd_map || n_rows < 0 || rows_per_map < 0 || pad_rows < 0)
+        return fail(h, RDP_E_INVALID, "rdp_doppler_stage_rows: bad argument");
     RDP_CUDA(h, cudaSetDevice(h->device));
-    return run_doppler(h, reinterpret_cast<const float2*>(x_rc), 0, rd_map, n_rows);
+    return run_doppler(h, reinterpret_cast<const float2*>(x_rc), 0, rd_map, n_rows, rows_per_map, pad_rows);
 }
 
 int rdp_cfar_stage_rows(rdp_handle* h, const float* rd_map, int32_t n_cpi, int32_t n_range_rows, float* cfar_out,
@@ -1136,6 +1169,16 @@ int rdp_copy_d2d(rdp_handle* h, void* dst, const void* src, size_t bytes) {
     if (!h || (!dst && bytes) || (!src && bytes)) return RDP_E_INVALID;
     RDP_CUDA(h, cudaSetDevice(h->device));
     RDP_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RDP_OK;
+}
+
+int rdp_copy_d2d_rows(rdp_handle* h, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes,
+                      size_t n_rows) {
+    if (!h || !dst || !src || row_bytes > dst_pitch || row_bytes > src_pitch) return RDP_E_INVALID;
+    if (!row_bytes || !n_rows) return RDP_OK;
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    RDP_CUDA(h, cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, n_rows, cudaMemcpyDeviceToDevice, h->stream));
     RDP_CUDA(h, cudaStreamSynchronize(h->stream));
     return RDP_OK;
 }

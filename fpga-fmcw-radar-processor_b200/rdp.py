@@ -87,13 +87,15 @@ SYMBOLS = {
     "rdp_fixed_magnitude": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "rdp_fixed_corner_turn": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP]),
     "rdp_range_stage_scatter": (C.c_int, [_VP, _VP, _I32, C.POINTER(RdpScatter)]),
-    "rdp_doppler_stage_rows": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
+    "rdp_doppler_stage_rows": (C.c_int, [_VP, _VP, C.c_int64, _I32, _I32, _VP]),
     "rdp_cfar_stage_rows": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "rdp_ipc_export": (C.c_int, [_VP, _VP, C.c_char_p]),
     "rdp_ipc_open": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
     "rdp_ipc_close": (C.c_int, [_VP, _VP]),
     "rdp_copy_d2d": (C.c_int, [_VP, _VP, _VP, _SZ]),
+    "rdp_copy_d2d_rows": (C.c_int, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _SZ]),
     "rdp_device_memset": (C.c_int, [_VP, _VP, C.c_int, _SZ]),
+    "rdp_gather_dets": (C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, C.POINTER(C.c_int64)]),
     "rdp_tracker_reset": (C.c_int, [_VP, C.POINTER(RdpTrackerConfig)]),
     "rdp_track_device": (C.c_int, [_VP, _VP, _VP, _I32, _VP, _VP, _VP]),
     "rdp_stream_open": (C.c_int, [_VP, _I32, _I32]),
@@ -155,16 +157,26 @@ class DeviceBuffer:
         self.core._check(self.core.lib.rdp_copy_h2d(self.core.h, self.ptr, _ptr(a), a.nbytes))
         return self
 
-    def download(self, shape, dtype) -> np.ndarray:
+    def download(self, shape, dtype, offset: int = 0) -> np.ndarray:
         out = np.empty(shape, dtype=dtype)
-        assert out.nbytes <= self.nbytes
-        self.core._check(self.core.lib.rdp_copy_d2h(self.core.h, _ptr(out), self.ptr, out.nbytes))
+        assert offset + out.nbytes <= self.nbytes
+        if out.nbytes:
+            self.core._check(self.core.lib.rdp_copy_d2h(self.core.h, _ptr(out), C.c_void_p(self.ptr.value + offset), out.nbytes))
         return out
 
     def free(self):
         if self.ptr is not None and self.core.h:
             self.core.lib.rdp_device_free(self.core.h, self.ptr)
         self.ptr = None
+
+
+class _BufferView:
+    """A DeviceBuffer seen from a byte offset (no ownership)."""
+
+    def __init__(self, buf, offset):
+        self.ptr, self.nbytes, self.core = C.c_void_p(buf.ptr.value + offset), buf.nbytes - offset, buf.core
+
+    download = DeviceBuffer.download
 
 
 class RadarCore:
@@ -326,10 +338,22 @@ class RadarCore:
                                                 d_dets.ptr, d_counts.ptr, d_status.ptr))
 
     def unpack_device_dets(self, d_dets: DeviceBuffer, d_counts: DeviceBuffer, n_cpi: int):
-        counts = d_counts.download((n_cpi,), np.int32)
-        rows = d_dets.download((n_cpi, self.max_dets_per_cpi), DET_DTYPE)
-        keep = [rows[i, :min(int(counts[i]), self.max_dets_per_cpi)] for i in range(n_cpi)]
-        return (np.concatenate(keep) if keep else np.zeros(0, DET_DTYPE)), counts
+        if n_cpi > self.max_cpis:                                    # the pack scratch holds max_cpis CPIs
+            parts = [self.unpack_device_dets(_BufferView(d_dets, i * self.max_dets_per_cpi * DET_DTYPE.itemsize),
+                                             _BufferView(d_counts, i * 4), min(self.max_cpis, n_cpi - i))
+                     for i in range(0, n_cpi, self.max_cpis)]
+            return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+        counts = np.zeros(n_cpi, np.int32)
+        if getattr(self, "_gather_buf", None) is None or len(self._gather_buf) < 1024:
+            self._gather_buf = np.empty(1024, DET_DTYPE)
+        total = C.c_int64()
+        peek = d_counts.download((n_cpi,), np.int32) if n_cpi else counts      # size the (reused) host buffer first
+        need = int(np.minimum(peek, self.max_dets_per_cpi).sum())
+        if need > len(self._gather_buf):
+            self._gather_buf = np.empty(max(need, 2 * len(self._gather_buf)), DET_DTYPE)
+        self._check(self.lib.rdp_gather_dets(self.h, d_dets.ptr, d_counts.ptr, n_cpi, _ptr(self._gather_buf), _ptr(counts),
+                                             C.byref(total)))
+        return self._gather_buf[:total.value].copy(), counts
 
     # -- stage taps (device work, host arrays in/out; for parity tests) -----------------------
     def range_stage(self, cube: np.ndarray) -> np.ndarray:

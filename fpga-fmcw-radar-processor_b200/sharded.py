@@ -69,6 +69,8 @@ class ShardedCpi:
         self.d_map = self.core_b.device_buffer(maps * self.rows_pad * n_chirps * 4)
         self.d_dets = self.core_b.device_buffer(n_cpi * max_dets_per_cpi * DET_DTYPE.itemsize)
         self.d_cnt, self.d_st = self.core_b.device_buffer(max(n_cpi * 4, 16)), self.core_b.device_buffer(max(n_cpi * 4, 16))
+        self.core_b._check(self.core_b.lib.rdp_device_memset(self.core_b.h, self.d_map.ptr, 0, self.d_map.nbytes))
+        self.core_b.sync()                                           # halo lines past the global edges stay 0
         self.peer_xrc = [None] * world
         self.peer_map = [None] * world
         self._opened = []
@@ -103,43 +105,48 @@ class ShardedCpi:
             self.peer_xrc[r], self.peer_map[r] = ptrs
 
     # -- phase C: range stage with the corner turn fused into peer stores -------------------------------
-    def range_scatter(self, cube_local: np.ndarray):
-        cube = self.core_a._as_cube(cube_local)                      # [cpi, channel, local chirp, sample(, 2)]
-        d_in = self.core_a.device_buffer(cube.nbytes).upload(cube)
+    def upload_local(self, cube_local: np.ndarray):
+        """This rank's chirps [cpi, channel, n_chirps / world, sample(, 2)] into a device buffer (caller frees)."""
+        cube = self.core_a._as_cube(cube_local)
+        if cube.shape[0] != self.n_cpi:
+            raise RdpError(-1, f"expected {self.n_cpi} CPIs, got {cube.shape[0]}")
+        return self.core_a.device_buffer(cube.nbytes).upload(cube)
+
+    def range_scatter_device(self, d_in):
         sc = RdpScatter()
         for r in range(self.world):
             sc.peer[r] = self.peer_xrc[r]
         sc.world, sc.rank = self.world, self.rank
+        self.core_a._check(self.core_a.lib.rdp_range_stage_scatter(self.core_a.h, d_in.ptr, self.n_cpi, C.byref(sc)))
+        self.core_a.sync()                                           # the peer stores have landed before the barrier
+
+    def range_scatter(self, cube_local: np.ndarray):
+        d_in = self.upload_local(cube_local)
         try:
-            self.core_a._check(self.core_a.lib.rdp_range_stage_scatter(self.core_a.h, d_in.ptr, cube.shape[0], C.byref(sc)))
-            self.core_a.sync()                                       # the peer stores have landed before the barrier
+            self.range_scatter_device(d_in)
         finally:
             d_in.free()
 
     # -- phase D: Doppler stage on the local range lines, into the halo-padded map ----------------------
     def doppler(self):
-        lib, h, nc = self.core_b.lib, self.core_b.h, self.n_chirps
-        self.core_b._check(lib.rdp_device_memset(h, self.d_map.ptr, 0, self.d_map.nbytes))   # global edges read 0
-        for m in range(self.maps):
-            src = C.c_void_p(self.d_xrc.ptr.value + m * self.rows_local * nc * 8)
-            dst = C.c_void_p(self.d_map.ptr.value + (m * self.rows_pad + self.halo) * nc * 4)
-            self.core_b._check(lib.rdp_doppler_stage_rows(h, src, self.rows_local, dst))
-        self.core_b.sync()
+        cb = self.core_b                                             # one launch: every map gets its halo lines left free
+        cb._check(cb.lib.rdp_doppler_stage_rows(cb.h, self.d_xrc.ptr, self.maps * self.rows_local, self.rows_local,
+                                                self.halo, self.d_map.ptr))
+        cb.sync()
 
     # -- phase E: CFAR halo lines from the neighbouring ranks' maps (device-to-device, over NVLink) ------
     def halo_exchange(self):
         lib, h, nc, hl = self.core_b.lib, self.core_b.h, self.n_chirps, self.halo
         if hl == 0:
             return
-        for m in range(self.maps):
-            base = (m * self.rows_pad) * nc * 4
-            if self.rank > 0:                                        # lines above mine = the last `hl` own lines of rank-1
-                src = self.peer_map[self.rank - 1] + base + (hl + self.rows_local - hl) * nc * 4
-                self.core_b._check(lib.rdp_copy_d2d(h, C.c_void_p(self.d_map.ptr.value + base), C.c_void_p(src), hl * nc * 4))
-            if self.rank < self.world - 1:                           # lines below mine = the first `hl` own lines of rank+1
-                src = self.peer_map[self.rank + 1] + base + hl * nc * 4
-                dst = self.d_map.ptr.value + base + (hl + self.rows_local) * nc * 4
-                self.core_b._check(lib.rdp_copy_d2d(h, C.c_void_p(dst), C.c_void_p(src), hl * nc * 4))
+        pitch, rowb = self.rows_pad * nc * 4, hl * nc * 4            # one call per neighbour: `maps` pieces of hl lines
+        if self.rank > 0:                                            # lines above mine = the last `hl` own lines of rank-1
+            src = self.peer_map[self.rank - 1] + self.rows_local * nc * 4
+            self.core_b._check(lib.rdp_copy_d2d_rows(h, self.d_map.ptr, pitch, C.c_void_p(src), pitch, rowb, self.maps))
+        if self.rank < self.world - 1:                               # lines below mine = the first `hl` own lines of rank+1
+            src = self.peer_map[self.rank + 1] + hl * nc * 4
+            dst = self.d_map.ptr.value + (hl + self.rows_local) * nc * 4
+            self.core_b._check(lib.rdp_copy_d2d_rows(h, C.c_void_p(dst), pitch, C.c_void_p(src), pitch, rowb, self.maps))
 
     # -- phase F: CFAR on own + halo lines; detections with global range indices ----------------------------
     def cfar(self):
@@ -176,6 +183,21 @@ class ShardedCpi:
         dets, _ = self.cfar()
         exchange.barrier()                                           # nobody reuses a buffer a neighbour still reads
         return dets, self.local_map()
+
+    def run_device(self, d_in, exchange):
+        """The same pipeline on a cube that is already on the device (`upload_local`); returns this rank's
+        detections only (the map stays on the device)."""
+        if self.peer_xrc[self.rank] is None:
+            self.connect(exchange.all_gather(self.export_handles()) if self.world > 1 else [self.export_handles()])
+            exchange.barrier()
+        self.range_scatter_device(d_in)
+        exchange.barrier()
+        self.doppler()
+        exchange.barrier()
+        self.halo_exchange()
+        dets, _ = self.cfar()
+        exchange.barrier()
+        return dets
 
     def close(self):
         for p in self._opened:

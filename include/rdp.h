@@ -251,20 +251,33 @@ int rdp_track_device(rdp_handle* h, const rdp_det* dets, const int32_t* n_dets, 
  *                            fused into K1's transposed store, no separate collective or repack); the caller
  *                            barriers across ranks before the Doppler stage reads
  *   rdp_doppler_stage_rows   Doppler stage on an explicit number of range lines (handle: n_chirps = the full
- *                            chirp count)
+ *                            chirp count); rows_per_map > 0 writes every group of rows_per_map lines with
+ *                            pad_rows untouched lines above and below it (room for the CFAR halo)
  *   rdp_cfar_stage_rows      CFAR stage on maps of an explicit number of range lines (own lines + halo lines
  *                            copied from the neighbouring ranks)
  *   rdp_ipc_export / open / close   CUDA IPC handles (64 opaque bytes) to map a peer rank's buffer
- *   rdp_copy_d2d, rdp_device_memset device-side copy (also from a mapped peer buffer) and fill            */
+ *   rdp_copy_d2d, rdp_copy_d2d_rows, rdp_device_memset   device-side copy (also from a mapped peer buffer;
+ *                            _rows: n_rows pieces of row_bytes at the given pitches, e.g. the halo lines of every
+ *                            map of a batch in one call) and fill                                              */
 int rdp_range_stage_scatter(rdp_handle* h, const void* cube, int32_t n_cpi, const rdp_scatter* sc);
-int rdp_doppler_stage_rows(rdp_handle* h, const void* x_rc, int64_t n_rows, float* rd_map);
+int rdp_doppler_stage_rows(rdp_handle* h, const void* x_rc, int64_t n_rows, int32_t rows_per_map, int32_t pad_rows,
+                           float* rd_map);
 int rdp_cfar_stage_rows(rdp_handle* h, const float* rd_map, int32_t n_cpi, int32_t n_range_rows, float* cfar_out,
                         rdp_det* dets, int32_t* n_dets, uint32_t* status);
 int rdp_ipc_export(rdp_handle* h, void* device_ptr, unsigned char handle_bytes[64]);
 int rdp_ipc_open(rdp_handle* h, const unsigned char handle_bytes[64], void** device_ptr);
 int rdp_ipc_close(rdp_handle* h, void* device_ptr);
 int rdp_copy_d2d(rdp_handle* h, void* dst_device, const void* src_device, size_t bytes);
+int rdp_copy_d2d_rows(rdp_handle* h, void* dst_device, size_t dst_pitch, const void* src_device, size_t src_pitch,
+                      size_t row_bytes, size_t n_rows);
 int rdp_device_memset(rdp_handle* h, void* dst_device, int value, size_t bytes);
+
+/* Device detection rows [n_cpi][max_dets_per_cpi] + per-CPI counts (as rdp_process_device / rdp_cfar_stage* leave
+ * them) -> one packed host list in (cpi, channel, range, doppler) order: dets_host needs room for
+ * sum(min(count, max_dets_per_cpi)) records (at most n_cpi * max_dets_per_cpi), n_cpi <= max_cpis.  The non-zero
+ * filter's output FIFO read side (rtl/src/radar_core.vhd:396-418).                                                */
+int rdp_gather_dets(rdp_handle* h, const rdp_det* dets_device, const int32_t* n_dets_device, int32_t n_cpi,
+                    rdp_det* dets_host, int32_t* counts_host, int64_t* total);
 
 /* Device / pinned-host memory owned by the caller (so a ctypes host needs no other CUDA binding). */
 int rdp_device_alloc(rdp_handle* h, size_t bytes, void** ptr);
