@@ -38,6 +38,8 @@ struct K1Launcher {
     void (*launch)(int grid, size_t smem, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
                    const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc);
 };
+constexpr int kStreamSpecDets = 24576;      // per CPI: head of the detection list a streaming slot copies back unasked
+
 struct K2Launcher {
     int T, G;
     size_t smem;
@@ -206,6 +208,7 @@ K3Launcher k3_for(int hl, int hc, int gl, int gc) {
 struct StreamSlot {
     cudaStream_t copy = nullptr;            // H2D of the cube and D2H of the results
     cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+    long long spec = 0;                     // records copied back speculatively with the counts
     void* d_in = nullptr;
     rdp_det* d_dets = nullptr;
     rdp_det* d_packed = nullptr;
@@ -229,7 +232,7 @@ struct rdp_handle {
     cudaEvent_t ev_map_ready[2] = {nullptr, nullptr}, ev_cfar_done[2] = {nullptr, nullptr};
     int overlap = 1;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
-    std::vector<cudaEvent_t> ev_copied, ev_done, ev_mapout;
+    std::vector<cudaEvent_t> ev_copied, ev_done, ev_mapout, ev_counts;
     float *win_r = nullptr, *win_d = nullptr;
     float2 *tw_r = nullptr, *tw_d = nullptr;
     float2* x_rc = nullptr;        // [chunk][channel][range][chirp]
@@ -437,10 +440,10 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
 
 __global__ void __launch_bounds__(256)
 k5_pack_dets_kernel(const rdp_det* __restrict__ dets, const int* __restrict__ counts, rdp_det* __restrict__ packed,
-                    int max_dets, int cpi_offset) {
-    // one CTA per CPI: offset = sum of the clipped counts of the CPIs before it
+                    int max_dets, int cpi_offset, int cpi_first) {
+    // one CTA per CPI (cpi_first + blockIdx.x): offset = sum of the clipped counts of the CPIs before it
     __shared__ long long offset_sh;
-    const int cpi = blockIdx.x;
+    const int cpi = cpi_first + blockIdx.x;
     if (threadIdx.x == 0) {
         long long off = 0;
         for (int i = 0; i < cpi; ++i) off += counts[i] < max_dets ? counts[i] : max_dets;
@@ -505,6 +508,7 @@ void release(rdp_handle* h) {
     for (auto e : h->ev_copied) cudaEventDestroy(e);
     for (auto e : h->ev_done) cudaEventDestroy(e);
     for (auto e : h->ev_mapout) cudaEventDestroy(e);
+    for (auto e : h->ev_counts) cudaEventDestroy(e);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
@@ -695,6 +699,7 @@ int ensure_host_path(rdp_handle* h) {
         RDP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDefault)); h->ev_copied.push_back(e);
         RDP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDefault)); h->ev_done.push_back(e);
         RDP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDefault)); h->ev_mapout.push_back(e);
+        RDP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDefault)); h->ev_counts.push_back(e);
     }
     return RDP_OK;
 }
@@ -897,7 +902,21 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
     if (rc) return rc;
     const size_t cells = cells_per_cpi(c);
     const size_t in_stride = cells * in_bytes_per_sample(c);
-    int k = 0;
+    // The detection list goes back chunk by chunk on the D2H stream while later chunks are still being copied in
+    // (PCIe is full duplex): after chunk k is queued, the host waits for the counts of chunk k-1 -- long finished,
+    // its successor's input copy takes several times its compute -- and queues the copy of its packed records.
+    long long list_off = 0;
+    auto drain = [&](int base0, int n0, int b0) -> int {
+        RDP_CUDA(h, cudaEventSynchronize(h->ev_counts[b0]));
+        long long total = 0;
+        for (int i = base0; i < base0 + n0; ++i) total += n_dets[i] < c.max_dets_per_cpi ? n_dets[i] : c.max_dets_per_cpi;
+        if (total > 0)
+            RDP_CUDA(h, cudaMemcpyAsync(dets + list_off, h->packed + list_off, sizeof(rdp_det) * (size_t)total,
+                                        cudaMemcpyDeviceToHost, h->d2h_stream));
+        list_off += total;
+        return RDP_OK;
+    };
+    int k = 0, prev_base = 0, prev_n = 0;
     for (int base = 0; base < n_cpi; base += h->chunk, ++k) {
         const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
         const int b = k & 1;
@@ -923,20 +942,24 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
                                         cudaMemcpyDeviceToHost, h->d2h_stream));
             RDP_CUDA(h, cudaEventRecord(h->ev_mapout[b], h->d2h_stream));
         }
+        // pack this chunk's records behind those of the chunks before it; counts / status to the host
+        h->launches += 1;
+        RDP_LAUNCH(k5_pack_dets_kernel, n, 256, 0, h->stream, h->dets, h->counts, h->packed, c.max_dets_per_cpi, 0, base);
+        rc = launch_check(h, "k5_pack_dets_kernel");
+        if (rc) return rc;
+        RDP_CUDA(h, cudaMemcpyAsync(n_dets + base, h->counts + base, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        RDP_CUDA(h, cudaMemcpyAsync(status + base, h->status + base, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        RDP_CUDA(h, cudaEventRecord(h->ev_counts[b], h->stream));
+        if (k >= 1) {
+            rc = drain(prev_base, prev_n, b ^ 1);
+            if (rc) return rc;
+        }
+        prev_base = base; prev_n = n;
     }
-    h->launches += 1;
-    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, h->dets, h->counts, h->packed, c.max_dets_per_cpi, 0);
-    rc = launch_check(h, "k5_pack_dets_kernel");
+    rc = drain(prev_base, prev_n, (k - 1) & 1);
     if (rc) return rc;
-    RDP_CUDA(h, cudaMemcpyAsync(n_dets, h->counts, sizeof(int) * (size_t)n_cpi, cudaMemcpyDeviceToHost, h->stream));
-    RDP_CUDA(h, cudaMemcpyAsync(status, h->status, sizeof(uint32_t) * (size_t)n_cpi, cudaMemcpyDeviceToHost, h->stream));
+    RDP_CUDA(h, cudaStreamSynchronize(h->d2h_stream));
     RDP_CUDA(h, cudaStreamSynchronize(h->stream));
-    long long total = 0;
-    for (int i = 0; i < n_cpi; ++i) total += n_dets[i] < c.max_dets_per_cpi ? n_dets[i] : c.max_dets_per_cpi;
-    if (total > 0)
-        RDP_CUDA(h, cudaMemcpyAsync(dets, h->packed, sizeof(rdp_det) * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
-    RDP_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (rd_map) RDP_CUDA(h, cudaStreamSynchronize(h->d2h_stream));
     return RDP_OK;
 }
 
@@ -955,7 +978,7 @@ int rdp_gather_dets(rdp_handle* h, const rdp_det* dets, const int32_t* n_dets, i
         int rc0 = dev_alloc(h, &h->packed, (size_t)c.max_cpis * c.max_dets_per_cpi);
         if (rc0) return rc0;
     }
-    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, dets, n_dets, h->packed, c.max_dets_per_cpi, 0);
+    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, dets, n_dets, h->packed, c.max_dets_per_cpi, 0, 0);
     int rc = launch_check(h, "k5_pack_dets_kernel");
     if (rc) return rc;
     RDP_CUDA(h, cudaMemcpyAsync(counts_host, n_dets, sizeof(int) * (size_t)n_cpi, cudaMemcpyDeviceToHost, h->stream));
@@ -1240,16 +1263,23 @@ int rdp_stream_submit(rdp_handle* h, int32_t slot, const void* cube, int32_t n_c
     rc = run_cfar(h, h->map_scratch[0], n_cpi, nullptr, sl.d_dets, sl.d_counts, sl.d_status, 0);
     if (rc) return rc;
     h->launches += 1;
-    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, sl.d_dets, sl.d_counts, sl.d_packed, c.max_dets_per_cpi, 0);
+    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, sl.d_dets, sl.d_counts, sl.d_packed, c.max_dets_per_cpi, 0, 0);
     rc = launch_check(h, "k5_pack_dets_kernel");
     if (rc) return rc;
     RDP_CUDA(h, cudaEventRecord(sl.ev_done, h->stream));
     RDP_CUDA(h, cudaStreamWaitEvent(sl.copy, sl.ev_done, 0));
     RDP_CUDA(h, cudaMemcpyAsync(sl.h_counts, sl.d_counts, sizeof(int) * (size_t)n_cpi, cudaMemcpyDeviceToHost, sl.copy));
     RDP_CUDA(h, cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(uint32_t) * (size_t)n_cpi, cudaMemcpyDeviceToHost, sl.copy));
-    // the packed list is copied at full capacity so that one synchronisation suffices (slot_cpis is small)
-    RDP_CUDA(h, cudaMemcpyAsync(sl.h_packed, sl.d_packed, sizeof(rdp_det) * (size_t)n_cpi * c.max_dets_per_cpi,
-                                cudaMemcpyDeviceToHost, sl.copy));
+    // the head of the packed list is copied speculatively together with the counts, so that one synchronisation
+    // suffices for ordinary scenes; rdp_stream_wait fetches the rest of an unusually long list
+    {
+        size_t spec = (size_t)n_cpi * c.max_dets_per_cpi;
+        int per_cpi = kStreamSpecDets;
+        if (const char* e = std::getenv("RDP_STREAM_SPEC")) per_cpi = std::atoi(e) > 0 ? std::atoi(e) : per_cpi;   // tests
+        if (spec > (size_t)n_cpi * per_cpi) spec = (size_t)n_cpi * per_cpi;
+        sl.spec = (long long)spec;
+        RDP_CUDA(h, cudaMemcpyAsync(sl.h_packed, sl.d_packed, sizeof(rdp_det) * spec, cudaMemcpyDeviceToHost, sl.copy));
+    }
     RDP_CUDA(h, cudaEventRecord(sl.ev_out, sl.copy));
     sl.n_cpi = n_cpi;
     sl.busy = true;
@@ -1267,6 +1297,11 @@ int rdp_stream_wait(rdp_handle* h, int32_t slot, const rdp_det** dets, const int
     long long t = 0;
     for (int i = 0; i < sl.n_cpi; ++i)
         t += sl.h_counts[i] < h->cfg.max_dets_per_cpi ? sl.h_counts[i] : h->cfg.max_dets_per_cpi;
+    if (t > sl.spec) {
+        RDP_CUDA(h, cudaMemcpyAsync(sl.h_packed + sl.spec, sl.d_packed + sl.spec, sizeof(rdp_det) * (size_t)(t - sl.spec),
+                                    cudaMemcpyDeviceToHost, sl.copy));
+        RDP_CUDA(h, cudaStreamSynchronize(sl.copy));
+    }
     if (dets) *dets = sl.h_packed;
     if (n_dets) *n_dets = sl.h_counts;
     if (status) *status = sl.h_status;

@@ -223,8 +223,19 @@ def case_cfar_fixed_tb_map(make_core):
         assert (30, 16) in cells and (50, 8) in cells and counts[0] >= 2
 
 
-def case_streaming(make_core, n_samples=64, n_chirps=32, n_sub=7, n_slots=3):
-    """Streaming ingest (BASELINE config 5): results of pipelined single-CPI submissions equal the batch API's."""
+def case_streaming(make_core, n_samples=64, n_chirps=32, n_sub=7, n_slots=3, spec=None):
+    """Streaming ingest (BASELINE config 5): results of pipelined single-CPI submissions equal the batch API's.
+    `spec` shrinks the speculatively copied head of the list so that the second copy in rdp_stream_wait runs."""
+    import os
+    if spec is not None:
+        os.environ["RDP_STREAM_SPEC"] = str(spec)
+    try:
+        _streaming(make_core, n_samples, n_chirps, n_sub, n_slots)
+    finally:
+        os.environ.pop("RDP_STREAM_SPEC", None)
+
+
+def _streaming(make_core, n_samples, n_chirps, n_sub, n_slots):
     cube, _ = st.synthetic_cube(n_sub, 2, n_chirps, n_samples, seed=41, sigma=25.0, n_targets=(1, 3))
     with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=2, max_cpis=n_sub, max_dets_per_cpi=4096) as c:
         ref, ref_counts = (x.copy() for x in c.process(cube, want_map=False)[1:3])

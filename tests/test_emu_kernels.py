@@ -85,6 +85,7 @@ def test_cfar_fixed_tb_map(make_core):
 
 def test_streaming(make_core):
     pc.case_streaming(make_core)
+    pc.case_streaming(make_core, spec=2)
 
 
 def test_fixed_stages(make_core):

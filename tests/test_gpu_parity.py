@@ -213,6 +213,7 @@ def test_device_resident_api_matches_host_api(make_core):
 def test_streaming(make_core):
     pc.case_streaming(make_core)
     pc.case_streaming(make_core, 512, 256, n_sub=5, n_slots=2)
+    pc.case_streaming(make_core, spec=2)
 
 
 def test_sharded_cpi_one_process(make_core):
