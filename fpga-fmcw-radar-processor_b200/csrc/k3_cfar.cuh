@@ -632,48 +632,87 @@ k3_cfar_generic_kernel(const float* __restrict__ rd_map, float* __restrict__ cfa
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: ordered compaction, two small kernels.  k4_row_offsets: one CTA per CPI counts the set bits
+// K4: ordered compaction, two small kernels.  k4_row_offsets: one 1024-thread CTA per CPI counts the set bits
 // of every range line of every channel and exclusive-scans them in (channel, range) order ->
 // per-line record offsets, the CPI's detection count and its status word.  k4_emit: one warp per
 // line writes the `r d mag` records (radar_core.vhd:396-418, TRUE coordinates) at its offset.
 // The list is canonical without a sort; records beyond max_dets are dropped (the LAST ones in
 // canonical order) and RDP_STATUS_DET_OVERFLOW is raised (status_overflow analogue, :447-456).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int K4_THREADS = 1024;
+
+__device__ __forceinline__ int k4_row_count(const uint32_t* __restrict__ bm, int r, int words_per_row) {
+    const uint32_t* p = bm + (long long)r * words_per_row;
+    int n = 0;
+    if ((words_per_row & 3) == 0) {
+        for (int w = 0; w < words_per_row; w += 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + w));
+            n += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        }
+    } else {
+        for (int w = 0; w < words_per_row; ++w) n += __popc(__ldg(p + w));
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
 k4_row_offsets_kernel(const uint32_t* __restrict__ det_bits, int* __restrict__ row_off, int* __restrict__ counts,
                       uint32_t* __restrict__ status, CfarArgs a) {
-    __shared__ int warp_sum[8];
-    __shared__ int carry_sh;
+    // every thread owns `per` consecutive lines; one block-wide exclusive scan of the per-thread totals
+    __shared__ int warp_sum[K4_THREADS / 32];
     const int cpi = blockIdx.x;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int rows = a.n_channels * a.n_range;
     const uint32_t* bm = det_bits + (long long)cpi * rows * a.words_per_row;
     int* off = row_off + (long long)cpi * rows;
-    if (threadIdx.x == 0) carry_sh = 0;
-    __syncthreads();
-    for (int r0 = 0; r0 < rows; r0 += 256) {
-        const int r = r0 + threadIdx.x;
-        int n = 0;
-        if (r < rows)
-            for (int w = 0; w < a.words_per_row; ++w) n += __popc(__ldg(bm + (long long)r * a.words_per_row + w));
-        int incl = n;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        int base = carry_sh;
-        for (int i = 0; i < warp; ++i) base += warp_sum[i];
-        if (r < rows) off[r] = base + incl - n;
-        __syncthreads();
-        if (threadIdx.x == 255) carry_sh = base + incl;
-        __syncthreads();
+    const int per = (rows + K4_THREADS - 1) / K4_THREADS;
+    const int r_begin = threadIdx.x * per;
+    constexpr int KEEP = 8;                                       // line counts kept in registers (loads all in flight)
+    int n[KEEP];
+    int tot = 0;
+    RDP_UNROLL
+    for (int i = 0; i < KEEP; ++i) {
+        const int r = r_begin + i;
+        n[i] = (i < per && r < rows) ? k4_row_count(bm, r, a.words_per_row) : 0;
+        tot += n[i];
     }
-    if (threadIdx.x == 0) {
-        const int total = carry_sh;
-        counts[cpi] = total;
-        status[cpi] = total > a.max_dets ? (uint32_t)RDP_STATUS_DET_OVERFLOW : 0u;
+    for (int i = KEEP; i < per; ++i) {
+        const int r = r_begin + i;
+        if (r < rows) tot += k4_row_count(bm, r, a.words_per_row);
+    }
+    int incl = tot;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_sum[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        warp_sum[lane] = v;
+    }
+    __syncthreads();
+    int base = (warp > 0 ? warp_sum[warp - 1] : 0) + incl - tot;
+    RDP_UNROLL
+    for (int i = 0; i < KEEP; ++i) {
+        const int r = r_begin + i;
+        if (i < per && r < rows) off[r] = base;
+        base += n[i];
+    }
+    for (int i = KEEP; i < per; ++i) {
+        const int r = r_begin + i;
+        if (r < rows) {
+            off[r] = base;
+            base += k4_row_count(bm, r, a.words_per_row);
+        }
+    }
+    if (threadIdx.x == K4_THREADS - 1) {
+        counts[cpi] = base;
+        status[cpi] = base > a.max_dets ? (uint32_t)RDP_STATUS_DET_OVERFLOW : 0u;
     }
 }
 

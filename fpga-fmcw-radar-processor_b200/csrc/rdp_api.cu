@@ -426,7 +426,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     int rc = launch_check(h, "k3_cfar_kernel");
     if (rc) return rc;
     stage_begin(h, 3);
-    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, 256, 0, h->cur, h->det_bits, h->row_off, counts, status, args);
+    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, K4_THREADS, 0, h->cur, h->det_bits, h->row_off, counts, status, args);
     const long long total_rows = maps * c.n_samples;
     int lanes_per_row = 1;
     while (lanes_per_row < args.words_per_row && lanes_per_row < 32) lanes_per_row <<= 1;
