@@ -7,6 +7,14 @@
 // range-major ([range][chirp], corner_turner.vhd:79-80) as TC*8-byte contiguous segments,
 // so the transpose costs no extra pass over HBM.
 //   algorithmic HBM bytes / cell: B_in (4 int16-IQ | 8 complex64) read + 8 written.
+//
+// Long chirps (2048 / 4096 samples) leave room for only 8 / 4 chirps of a tile in one SM's shared memory, i.e.
+// 64- / 32-byte output segments.  For those the kernel runs as thread-block CLUSTERS of CS = 2 / 4 CTAs: each
+// CTA transforms its own TC_MAX chirps but owns N / CS range bins of the cluster's CS * TC_MAX chirps -- the
+// spectra are written straight into the owning CTA's shared memory (distributed shared memory,
+// st.shared::cluster), so every CTA stores 128-byte segments.  Measured on B200 this only pays when the segments
+// are peer stores over NVLink (sharded mode, +15 %); into local HBM the 8-byte remote shared-memory stores cost
+// more than the short segments did (2.4x slower), so the host uses the plain kernel there.
 #pragma once
 #include "fft_core.cuh"
 
@@ -21,7 +29,32 @@ struct K1Shape {
     static __host__ __device__ constexpr size_t smem_bytes(int tile_chirps) {
         return sizeof(float2) * ((size_t)Plan::N * (tile_chirps + 1) + (size_t)G * Plan::XBUFS);
     }
+    // cluster variant: CS CTAs, each holding N / CS range bins of CS * TC_MAX chirps
+    static constexpr int CS = (Plan::N == 4096) ? 4 : (Plan::N == 2048 ? 2 : 1);
+    static constexpr int CL_ROWS = Plan::N / CS, CL_COLS = CS * TC_MAX, CL_PITCH = CL_COLS + 1;
+    static __host__ __device__ constexpr size_t smem_bytes_cluster() {
+        return sizeof(float2) * ((size_t)CL_ROWS * CL_PITCH + (size_t)G * Plan::XBUFS);
+    }
 };
+
+#ifndef RDP_EMU
+__device__ __forceinline__ uint32_t k1_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t k1_mapa(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void k1_st_cluster(uint32_t addr, float2 v) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void k1_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+#endif
 
 // raw sample word(s) of one thread for one chirp: int16 IQ = one 32-bit word {Q[31:16], I[15:0]}
 // (window_multiplier.vhd:93-94), complex64 = one float2
@@ -179,5 +212,121 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
         __syncthreads();
     }
 }
+
+#ifndef RDP_EMU
+// Cluster variant (CS = K1Shape::CS > 1).  Launch with cluster dimension (CS, 1, 1); tiles_per_map (tiles of TC_MAX
+// chirps) must be a multiple of CS.  total_tiles counts TC_MAX-chirp tiles as in the plain kernel.
+template <class Plan, int IN_FMT>
+__global__ void __launch_bounds__(K1Shape<Plan>::THREADS)
+k1_range_cluster_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
+                        const float* __restrict__ window, const float2* __restrict__ twtab,
+                        int n_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc) {
+    using Sh = K1Shape<Plan>;
+    constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
+    constexpr int G = Sh::G, THREADS = Sh::THREADS, TCM = Sh::TC_MAX, CS = Sh::CS;
+    constexpr int ROWS = Sh::CL_ROWS, COLS = Sh::CL_COLS, PITCH = Sh::CL_PITCH;
+    static_assert(CS > 1 && (COLS % 2) == 0, "cluster variant");
+    using P0 = typename Plan::P0;
+    using PL = typename Plan::LAST;
+    using Raw = K1Raw<IN_FMT>;
+    RDP_DYN_SMEM(smem_raw);
+    float2* tile = reinterpret_cast<float2*>(smem_raw);                      // [ROWS][PITCH]: my range bins, the cluster's chirps
+    float2* xbuf = tile + (size_t)ROWS * PITCH + (size_t)(threadIdx.x / T) * Plan::XBUFS;
+    const int tid = threadIdx.x % T, gid = threadIdx.x / T;
+    const int rank = (int)k1_cluster_rank();
+    const int cid = blockIdx.x / CS, n_clusters = gridDim.x / CS;
+    // the same tile in every CTA of the cluster (shared::cluster window addresses)
+    uint32_t peer_tile[CS];
+    RDP_UNROLL
+    for (int r = 0; r < CS; ++r) peer_tile[r] = k1_mapa((uint32_t)__cvta_generic_to_shared(tile), (uint32_t)r);
+
+    float2 tw[Plan::NTW > 0 ? Plan::NTW : 1];
+    Plan::load_twiddles(tw, twtab, tid);
+    float wv[E];
+    RDP_UNROLL
+    for (int b = 0; b < P0::NB; ++b) {
+        RDP_UNROLL
+        for (int r = 0; r < P0::R; ++r) wv[b * P0::R + r] = __ldg(window + P0::in_index(tid, b, r));
+    }
+    int parity = 0;
+    constexpr int ITERS = (TCM + G - 1) / G;
+    const int n_ctiles = (int)(total_tiles / CS);                          // cluster tiles of CS * TCM chirps
+    const int ctiles_per_map = tiles_per_map / CS;
+
+    typename Raw::T raw[E];
+    auto fetch = [&](int ct, int it) {
+        const int c = it * G + gid;
+        const bool ok = ct < n_ctiles && c < TCM;
+        const int mp = ct / ctiles_per_map;
+        const int chirp = mp * n_chirps + (ct - mp * ctiles_per_map) * COLS + rank * TCM + c;
+        const long long first = (long long)chirp * N + tid;
+        RDP_UNROLL
+        for (int b = 0; b < P0::NB; ++b) {
+            RDP_UNROLL
+            for (int r = 0; r < P0::R; ++r)
+                raw[b * P0::R + r] = ok ? Raw::load(cube, first + (b * T + r * (N / P0::R))) : Raw::zero();
+        }
+    };
+    fetch(cid, 0);
+    k1_cluster_sync();                                                     // every CTA of the cluster is running
+
+    for (int ct = cid; ct < n_ctiles; ct += n_clusters) {
+        const int mp = ct / ctiles_per_map;
+        const long long map = mp;
+        const int c0 = (ct - mp * ctiles_per_map) * COLS;                   // first chirp of the cluster tile
+        for (int it = 0; it < ITERS; ++it) {
+            const int c = it * G + gid;
+            const bool active = c < TCM;
+            float2 v[E];
+            RDP_UNROLL
+            for (int i = 0; i < E; ++i) {
+                const float2 s = Raw::cvt(raw[i]);
+                v[i] = make_float2(s.x * wv[i], s.y * wv[i]);
+            }
+            if (it + 1 < ITERS) fetch(ct, it + 1);
+            else fetch(ct + n_clusters, 0);
+            Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
+            if (active) {
+                const uint32_t col_off = (uint32_t)(rank * TCM + c) * 8u;
+                RDP_UNROLL
+                for (int b = 0; b < PL::NB; ++b) {
+                    RDP_UNROLL
+                    for (int r = 0; r < PL::R; ++r) {
+                        const int k = PL::out_index(tid, b, r);            // range bin: owner CTA k / ROWS, its row k % ROWS
+                        const int owner = k / ROWS;
+                        uint32_t base = peer_tile[0];
+                        RDP_UNROLL
+                        for (int q = 1; q < CS; ++q) base = owner == q ? peer_tile[q] : base;
+                        k1_st_cluster(base + (uint32_t)(k % ROWS) * (PITCH * 8u) + col_off, v[b * PL::R + r]);
+                    }
+                }
+            }
+        }
+        k1_cluster_sync();                                                 // all spectra of the cluster tile have landed
+        {
+            constexpr int HALF = COLS / 2, KSTEP = THREADS / HALF;
+            const int c = (threadIdx.x % HALF) * 2;
+            if (sc.world > 1) {
+                const int rows_local = 1 << sc.rows_shift;
+                const long long col0 = (long long)sc.rank * n_chirps + c0 + c;
+                for (int r = threadIdx.x / HALF; r < ROWS; r += KSTEP) {
+                    const int k = rank * ROWS + r;
+                    float2* row = sc.peer[k >> sc.rows_shift] +
+                                  (map * rows_local + (k & (rows_local - 1))) * (long long)sc.n_chirps_total + col0;
+                    const float2 a = tile[r * PITCH + c], b2 = tile[r * PITCH + c + 1];
+                    *reinterpret_cast<float4*>(row) = make_float4(a.x, a.y, b2.x, b2.y);
+                }
+            } else {
+                float2* dst = x_rc + map * (long long)N * n_chirps + (long long)rank * ROWS * n_chirps + c0 + c;
+                for (int r = threadIdx.x / HALF; r < ROWS; r += KSTEP) {
+                    const float2 a = tile[r * PITCH + c], b2 = tile[r * PITCH + c + 1];
+                    *reinterpret_cast<float4*>(dst + (long long)r * n_chirps) = make_float4(a.x, a.y, b2.x, b2.y);
+                }
+            }
+        }
+        k1_cluster_sync();                                                 // nobody overwrites a tile that is still being stored
+    }
+}
+#endif
 
 }  // namespace rdp

@@ -37,6 +37,13 @@ struct K1Launcher {
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(int grid, size_t smem, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
                    const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc);
+    // thread-block-cluster variant for long chirps (cs = CTAs per cluster; 1 = none)
+    int cs;
+    size_t smem_cluster;
+    cudaError_t (*prepare_cluster)(size_t smem, int* max_clusters);
+    cudaError_t (*launch_cluster)(int n_clusters, size_t smem, cudaStream_t st, const void* cube, float2* x_rc,
+                                  const float* win, const float2* tw, int n_chirps, int tiles_per_map,
+                                  long long total_tiles, K1Scatter sc);
 };
 constexpr int kStreamSpecDets = 24576;      // per CPI: head of the detection list a streaming slot copies back unasked
 
@@ -87,9 +94,58 @@ struct K1Inst {
         RDP_LAUNCH((k1_range_kernel<Plan, FMT>), grid, K1Shape<Plan>::THREADS, s, st, cube, x_rc, win, tw,
                    n_chirps, tile_chirps, tiles_per_map, total_tiles, sc);
     }
-    static K1Launcher get() {
-        return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch};
+#ifndef RDP_EMU
+    static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int n_clusters, size_t s, cudaStream_t st) {
+        std::memset(cfg, 0, sizeof(*cfg));
+        cfg->gridDim = dim3((unsigned)(n_clusters * K1Shape<Plan>::CS));
+        cfg->blockDim = dim3(K1Shape<Plan>::THREADS);
+        cfg->dynamicSmemBytes = s;
+        cfg->stream = st;
+        attr->id = cudaLaunchAttributeClusterDimension;
+        attr->val.clusterDim.x = K1Shape<Plan>::CS;
+        attr->val.clusterDim.y = 1;
+        attr->val.clusterDim.z = 1;
+        cfg->attrs = attr;
+        cfg->numAttrs = 1;
     }
+    static cudaError_t prepare_cluster(size_t s, int* max_clusters) {
+        if constexpr (K1Shape<Plan>::CS > 1) {
+            cudaError_t e = cudaFuncSetAttribute(k1_range_cluster_kernel<Plan, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s);
+            if (e != cudaSuccess) return e;
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute attr;
+            cluster_config(&cfg, &attr, 1, s, nullptr);
+            int n = 0;
+            e = cudaOccupancyMaxActiveClusters(&n, k1_range_cluster_kernel<Plan, FMT>, &cfg);
+            *max_clusters = n;
+            return e;
+        } else {
+            *max_clusters = 0;
+            return cudaSuccess;
+        }
+    }
+    static cudaError_t launch_cluster(int n_clusters, size_t s, cudaStream_t st, const void* cube, float2* x_rc,
+                                      const float* win, const float2* tw, int n_chirps, int tiles_per_map,
+                                      long long total_tiles, K1Scatter sc) {
+        if constexpr (K1Shape<Plan>::CS > 1) {
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute attr;
+            cluster_config(&cfg, &attr, n_clusters, s, st);
+            return cudaLaunchKernelEx(&cfg, k1_range_cluster_kernel<Plan, FMT>, cube, x_rc, win, tw, n_chirps, tiles_per_map,
+                                      total_tiles, sc);
+        } else {
+            return cudaErrorNotSupported;
+        }
+    }
+    static K1Launcher get() {
+        return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch,
+                          K1Shape<Plan>::CS, K1Shape<Plan>::smem_bytes_cluster(), &prepare_cluster, &launch_cluster};
+    }
+#else
+    static K1Launcher get() {
+        return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch, 1, 0, nullptr, nullptr};
+    }
+#endif
 };
 
 template <class Plan, int MAG>
@@ -257,6 +313,7 @@ struct rdp_handle {
     int cfar_tma = 0;               // last CFAR launch staged its tiles with TMA
     int k1_tile_chirps = 1;
     size_t k1_smem = 0;
+    int k1_max_clusters = 0;       // > 0: the cluster variant of K1 is usable for this shape
     CfarArgs cfar;
     TrackState* trk_state = nullptr;   // one track file per channel
     TrackerArgs trk_args;
@@ -345,7 +402,20 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1
         return fail(h, RDP_E_CAPACITY, "range stage: too many chirps in one launch; lower chunk_cpis");
     int grid = (int)(total < h->k1_grid_cap ? total : h->k1_grid_cap);
     stage_begin(h, 0);
-    h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total, sc);
+    // The cluster variant pays for its 128-byte segments with 8-byte distributed-shared-memory stores: measured 2.4x
+    // slower than the plain kernel into local HBM (1024 x 4096: 45 vs 19 ms per 1024 CPIs), 15 % faster when the
+    // segments are peer stores over NVLink (profiles/r1_summary.md) -- so it serves the sharded mode only.
+    // RDP_K1_CLUSTER=0 / 1 forces it off / on (A/B measurements).
+    bool use_cluster = h->k1_max_clusters > 0 && sc.world > 1;
+    if (const char* e = std::getenv("RDP_K1_CLUSTER")) use_cluster = h->k1_max_clusters > 0 && std::atoi(e) != 0;
+    if (use_cluster) {
+        const long long ctiles = total / h->k1.cs;
+        const int n_clusters = (int)(ctiles < h->k1_max_clusters ? ctiles : h->k1_max_clusters);
+        RDP_CUDA(h, h->k1.launch_cluster(n_clusters, h->k1.smem_cluster, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps,
+                                         tiles_per_map, total, sc));
+    } else {
+        h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total, sc);
+    }
     stage_end(h);
     return launch_check(h, "k1_range_kernel");
 }
@@ -583,6 +653,13 @@ int init_handle(rdp_handle* h) {
     int occ = 1;
     RDP_CUDA(h, h->k1.prepare(h->k1_smem, &occ));
     h->k1_grid_cap = h->sm_count * occ;
+    h->k1_max_clusters = 0;
+    if (h->k1.cs > 1 && h->k1.prepare_cluster && h->k1_tile_chirps == h->k1.tc_max &&
+        (c.n_chirps / h->k1.tc_max) % h->k1.cs == 0) {
+        int n = 0;
+        if (h->k1.prepare_cluster(h->k1.smem_cluster, &n) == cudaSuccess && n > 0) h->k1_max_clusters = n;
+        else cudaGetLastError();                                  // fall back to the plain kernel
+    }
     RDP_CUDA(h, h->k2.prepare(h->k2.smem, &occ));
     h->k2_grid_cap = h->sm_count * occ;
 

@@ -341,6 +341,37 @@ def case_cfar_random_config(make_core, seed):
             assert np.array_equal(dense_i[0], exp_i), kw
 
 
+def case_cfar_adaptive_stress(make_core, seed):
+    """The adaptive pre-filter threshold (window-sum bound, half-way exit) must never lose a detection: maps full
+    of ridges and isolated strong cells (windows whose mean is dominated by a few references, i.e. SCALE_MIN
+    territory), scales in any order, tiny / zero / huge magnitudes.  Bit-exact against the float oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    geo = [(4, 4, 2, 1), (3, 2, 1, 1), (2, 2, 1, 1), (8, 8, 4, 2)][seed % 4]
+    scales = [int(v) for v in rng.permutation([int(rng.integers(1, 3)), int(rng.integers(3, 5)), int(rng.integers(5, 8))])]
+    kw = dict(cfar_ref_r=geo[0], cfar_ref_d=geo[1], cfar_guard_r=geo[2], cfar_guard_d=geo[3],
+              rank_pct=int(rng.choice([25, 50, 75, 90])), scale_min=scales[0], scale_nom=scales[1], scale_max=scales[2],
+              cfar_axes=str(rng.choice(["as_built", "as_named"])), cfar_edges=str(rng.choice(["zero", "raster"])))
+    nr, nd = int(rng.choice([32, 64, 128])), int(rng.choice([64, 128, 256]))
+    m = rng.rayleigh(30.0, size=(2, nr, nd)).astype(np.float32)
+    for _ in range(6):                                               # ridges along either axis, of very different strength
+        a = float(10.0 ** rng.uniform(1.5, 4.5))
+        if rng.random() < 0.5:
+            m[int(rng.integers(0, 2)), int(rng.integers(0, nr)), :] += a * rng.random(nd).astype(np.float32)
+        else:
+            m[int(rng.integers(0, 2)), :, int(rng.integers(0, nd))] += a * rng.random(nr).astype(np.float32)
+    for _ in range(12):                                              # isolated strong cells and small plateaus
+        ch, r, d = int(rng.integers(0, 2)), int(rng.integers(0, nr)), int(rng.integers(0, nd))
+        m[ch, r:r + int(rng.integers(1, 4)), d:d + int(rng.integers(1, 4))] = float(10.0 ** rng.uniform(2.5, 6.0))
+    if seed % 3 == 0:
+        m[0] *= np.float32(1e-36)                                    # down into the bfloat16 subnormal range
+        m[1, : nr // 2] = 0.0                                        # a block of exact zeros
+    with make_core(n_range=nr, n_doppler=nd, n_channels=2, max_dets_per_cpi=1 << 15, **kw) as c:
+        dets, counts, status, dense = c.cfar_stage(m[None])
+        exp = np.stack([fp.cfar_stage(m[i], **kw) for i in range(2)])
+        assert np.array_equal(dense[0], exp), kw
+        assert counts[0] == np.count_nonzero(exp) and counts[0] > 0
+
+
 def _dets_from_scans(scans_per_channel):
     """scans_per_channel[cpi][channel] = list of (r, d, mag) in (range, doppler) order -> canonical list + counts."""
     import fpga_fmcw_radar_processor_b200 as rdp

@@ -111,3 +111,8 @@ def make_sharded(make_core):
 @pytest.mark.parametrize("world,kw", [(4, dict()), (2, dict(cfar_axes="as_named", mti_mode=2, input_format="int16"))])
 def test_sharded_cpi(make_sharded, make_core, world, kw):
     pc.case_sharded_cpi(make_sharded, make_core, world=world, **kw)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cfar_adaptive_stress(make_core, seed):
+    pc.case_cfar_adaptive_stress(make_core, seed)

@@ -118,6 +118,11 @@ def test_cfar_random_config(make_core, seed):
     pc.case_cfar_random_config(make_core, seed)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_cfar_adaptive_stress(make_core, seed):
+    pc.case_cfar_adaptive_stress(make_core, seed)
+
+
 def test_tracker(make_core):
     pc.case_tracker(make_core)
 
@@ -223,6 +228,8 @@ def test_sharded_cpi_one_process(make_core):
     pc.case_sharded_cpi(make_sharded, make_core, world=4)
     pc.case_sharded_cpi(make_sharded, make_core, world=8, n_chirps=256, n_samples=1024, n_ch=1, n_cpi=1,
                         cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2)
+    # 4096-sample chirps: the range stage runs as clusters of 4 CTAs (distributed shared memory) and scatters
+    pc.case_sharded_cpi(make_sharded, make_core, world=2, n_chirps=64, n_samples=4096, n_ch=1, n_cpi=2)
 
 
 def test_sharded_cpi_multi_gpu():
