@@ -87,9 +87,11 @@ __device__ __forceinline__ uint32_t bf16x2_lt_mask(uint32_t a, uint32_t b) {
     return r;
 #endif
 }
-// pre-filter reference value fl(v * s1) as float (int_mode: integer word, product rounded toward zero)
+// pre-filter reference value as float (int_mode: the integer word; below 2^24 the conversion is exact).  The
+// scale s1 is NOT applied to the references: 1 / s1 (with a 1e-3 margin) is folded into the per-cell threshold.
 __device__ __forceinline__ float cfar_scaled(float raw, float s1, bool int_mode) {
-    return int_mode ? __fmul_rz((float)(uint32_t)__float_as_int(raw), s1) : __fmul_rn(raw, s1);
+    (void)s1;
+    return int_mode ? (float)(uint32_t)__float_as_int(raw) : raw;
 }
 // bfloat16 truncation of v (>= 0), duplicated into both halves of a word
 __device__ __forceinline__ uint32_t bf16_dup(float v) {
@@ -399,7 +401,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     const int col = c0 + tx;
     uint32_t cb[4], cl[4], ch[4], acc[4];
     bool force[S];
-    float wsum[S];                                                // adaptive: bound of the window sum of each cell
+    float wsum[S];                                                // adaptive: pf_c x bound of the window sum of each cell
     if (a.adaptive) {
         // vertical pass of the box filter in registers: wsum[j] = sum_{k = j .. j + 2 HL} x[k], additions only
         const float* gp = grp + (ty * S) * Sh::NCG + ((tx + Sh::HCP - HC) >> 2);
@@ -410,19 +412,21 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             float common = x[S - 1];                              // lines S-1 .. 2 HL belong to every window
             RDP_UNROLL
             for (int k = S; k <= 2 * HL; ++k) common += x[k];
+            common *= a.pf_c;                                     // wsum comes out already times pf_c
             float part = 0.0f;
             wsum[S - 1] = common;
             RDP_UNROLL
-            for (int j = S - 2; j >= 0; --j) { part += x[j]; wsum[j] = common + part; }
+            for (int j = S - 2; j >= 0; --j) { part += x[j]; wsum[j] = fmaf(part, a.pf_c, common); }
             part = 0.0f;
             RDP_UNROLL
-            for (int j = 1; j < S; ++j) { part += x[2 * HL + j]; wsum[j] += part; }
+            for (int j = 1; j < S; ++j) { part += x[2 * HL + j]; wsum[j] = fmaf(part, a.pf_c, wsum[j]); }
         } else {
             RDP_UNROLL
             for (int j = 0; j < S; ++j) {
                 wsum[j] = 0.0f;
                 RDP_UNROLL
                 for (int k = 0; k <= 2 * HL; ++k) wsum[j] += x[j + k];
+                wsum[j] *= a.pf_c;
             }
         }
     }
@@ -432,8 +436,11 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         const float cut_hi = cfar_as_float(tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
         float c_lo = cut_lo, c_hi = cut_hi;
         if (a.adaptive) {
-            c_lo = fmaxf(c_lo * a.pf_a, fminf(c_lo * a.pf_b, wsum[2 * p] * a.pf_c));
-            c_hi = fmaxf(c_hi * a.pf_a, fminf(c_hi * a.pf_b, wsum[2 * p + 1] * a.pf_c));
+            c_lo = fmaxf(c_lo * a.pf_a, fminf(c_lo * a.pf_b, wsum[2 * p]));
+            c_hi = fmaxf(c_hi * a.pf_a, fminf(c_hi * a.pf_b, wsum[2 * p + 1]));
+        } else {
+            c_lo *= a.pf_a;
+            c_hi *= a.pf_a;
         }
         const uint32_t h0 = bf16_up(c_lo), h1 = bf16_up(c_hi);
         cb[p] = h0 | (h1 << 16);
@@ -441,8 +448,10 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         ch[p] = h1 << 16;
         acc[p] = 0u;
         // bfloat16 subnormal range: leave the decision to the exact phase
-        force[2 * p] = cut_lo > 0.0f && c_lo < 1e-36f;
-        force[2 * p + 1] = cut_hi > 0.0f && c_hi < 1e-36f;
+        // positive cuts so small that the threshold may fall into the bfloat16 subnormal range (pf_a >= 1e-6) go
+        // to the exact phase; one unsigned compare on the bit pattern covers 0 < cut < 1e-30
+        force[2 * p] = (uint32_t)__float_as_int(cut_lo) - 1u < 0x0da24260u - 1u;
+        force[2 * p + 1] = (uint32_t)__float_as_int(cut_hi) - 1u < 0x0da24260u - 1u;
     }
     const uint32_t* tp = th + (ty * S) * Sh::SCOLS + tx + Sh::HCP;
     for (int dc = -HC; dc <= 0; ++dc) {
@@ -472,14 +481,30 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             else K3Rows<HL, GL, false, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
         }
     }
-    RDP_UNROLL
-    for (int j = 0; j < S; ++j) {
-        const int line = r0 + ty * S + j;
-        if (line < a.n_range && col < a.n_doppler) {
-            const uint32_t lo16 = acc[j >> 1] & 0xffffu;
-            const uint32_t cnt = (j & 1) ? (((acc[j >> 1] >> 16) + lo16) & 0xffffu) : lo16;
-            if (cfar_out) cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)line * a.n_doppler + col] = 0.0f;
-            if ((int)cnt >= a.rank_idx + 1 || force[j]) surv[atomicAdd(n_surv, 1)] = (unsigned short)((ty * S + j) * TCOLS + tx);
+    {
+        // survivors of this strip as a bit mask; most strips have none and skip the list append altogether
+        uint32_t smask = 0u;
+        RDP_UNROLL
+        for (int p = 0; p < 4; ++p) {
+            const uint32_t lo16 = acc[p] & 0xffffu, hi16 = ((acc[p] >> 16) + lo16) & 0xffffu;
+            smask |= ((int)lo16 >= a.rank_idx + 1 || force[2 * p]) ? (1u << (2 * p)) : 0u;
+            smask |= ((int)hi16 >= a.rank_idx + 1 || force[2 * p + 1]) ? (2u << (2 * p)) : 0u;
+        }
+        const int lines_left = a.n_range - (r0 + ty * S);            // strips / columns past the edge of the map
+        if (col >= a.n_doppler || lines_left <= 0) smask = 0u;
+        else if (lines_left < S) smask &= (1u << lines_left) - 1u;
+        if (cfar_out && col < a.n_doppler) {
+            RDP_UNROLL
+            for (int j = 0; j < S; ++j)
+                if (j < lines_left) cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)(r0 + ty * S + j) * a.n_doppler + col] = 0.0f;
+        }
+        if (smask) {
+            int slot = atomicAdd(n_surv, __popc(smask));
+            while (smask) {
+                const int j = __ffs(smask) - 1;
+                smask &= smask - 1u;
+                surv[slot++] = (unsigned short)((ty * S + j) * TCOLS + tx);
+            }
         }
     }
     __syncthreads();

@@ -689,14 +689,16 @@ int init_handle(rdp_handle* h) {
         a.s1 = (float)c.scale_override;
     }
     if (a.adaptive) {
-        // detection => x_k < max(cut / smax, cut / snom, min(cut / smin, mean / 2)); times s1, with a 1e-3 margin
+        // detection => x_k < max(cut / smax, cut / snom, min(cut / smin, mean / 2)), each term with a 1e-3 margin
         const float big = a.snom < a.smax ? a.snom : a.smax;
-        a.pf_a = a.s1 / big * 1.001f;
-        a.pf_b = a.s1 / a.smin * 1.001f;
-        a.pf_c = 0.5f * a.s1 / (float)a.n_ref * 1.002f;
+        a.pf_a = 1.001f / big;
+        a.pf_b = 1.001f / a.smin;
+        a.pf_c = 0.5f * 1.002f / (float)a.n_ref;
     } else {
-        a.pf_a = 1.0f; a.pf_b = 0.0f; a.pf_c = 0.0f;
+        // fixed scale: fl(ref * s1) < cut  =>  ref < cut / s1 * (1 + 2^-23)
+        a.pf_a = 1.001f / a.s1; a.pf_b = 0.0f; a.pf_c = 0.0f;
     }
+    if (a.pf_a < 1e-6f) a.pf_a = 1e-6f;                            // keeps thresholds of cuts >= 1e-30 out of the bf16 subnormals
     a.raster = c.cfar_edges == RDP_EDGES_RASTER;
     a.int_mode = 0;
     a.is1 = (int)a.s1; a.ismin = c.scale_min; a.isnom = c.scale_nom; a.ismax = c.scale_max;
