@@ -400,7 +400,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     const int tx = threadIdx.x % TCOLS, ty = threadIdx.x / TCOLS;
     const int col = c0 + tx;
     uint32_t cb[4], cl[4], ch[4], acc[4];
-    bool force[S];
+    uint32_t fmask = 0u;                                          // bit j: cell j of the strip goes to the exact phase regardless
     float wsum[S];                                                // adaptive: pf_c x bound of the window sum of each cell
     if (a.adaptive) {
         // vertical pass of the box filter in registers: wsum[j] = sum_{k = j .. j + 2 HL} x[k], additions only
@@ -450,8 +450,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         // bfloat16 subnormal range: leave the decision to the exact phase
         // positive cuts so small that the threshold may fall into the bfloat16 subnormal range (pf_a >= 1e-6) go
         // to the exact phase; one unsigned compare on the bit pattern covers 0 < cut < 1e-30
-        force[2 * p] = (uint32_t)__float_as_int(cut_lo) - 1u < 0x0da24260u - 1u;
-        force[2 * p + 1] = (uint32_t)__float_as_int(cut_hi) - 1u < 0x0da24260u - 1u;
+        fmask |= ((uint32_t)__float_as_int(cut_lo) - 1u < 0x0da24260u - 1u) ? (1u << (2 * p)) : 0u;
+        fmask |= ((uint32_t)__float_as_int(cut_hi) - 1u < 0x0da24260u - 1u) ? (2u << (2 * p)) : 0u;
     }
     const uint32_t* tp = th + (ty * S) * Sh::SCOLS + tx + Sh::HCP;
     for (int dc = -HC; dc <= 0; ++dc) {
@@ -466,11 +466,11 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         constexpr int HALF_REFS = (HC - GC) * (2 * HL + 1) + (GC + 1) * (2 * HL - 2 * GL);
         const int need = HALF_REFS - (a.n_ref - a.rank_idx - 1);
         if (need > 0) {
-            bool mine = false;
+            bool mine = fmask != 0u;
             RDP_UNROLL
             for (int p = 0; p < 4; ++p) {
                 const uint32_t lo16 = acc[p] & 0xffffu, hi16 = ((acc[p] >> 16) + lo16) & 0xffffu;
-                mine = mine || (int)lo16 >= need || (int)hi16 >= need || force[2 * p] || force[2 * p + 1];
+                mine = mine || (int)lo16 >= need || (int)hi16 >= need;
             }
             go_on = __any_sync(0xffffffffu, mine);
         }
@@ -483,12 +483,12 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     }
     {
         // survivors of this strip as a bit mask; most strips have none and skip the list append altogether
-        uint32_t smask = 0u;
+        uint32_t smask = fmask;
         RDP_UNROLL
         for (int p = 0; p < 4; ++p) {
             const uint32_t lo16 = acc[p] & 0xffffu, hi16 = ((acc[p] >> 16) + lo16) & 0xffffu;
-            smask |= ((int)lo16 >= a.rank_idx + 1 || force[2 * p]) ? (1u << (2 * p)) : 0u;
-            smask |= ((int)hi16 >= a.rank_idx + 1 || force[2 * p + 1]) ? (2u << (2 * p)) : 0u;
+            smask |= ((int)lo16 >= a.rank_idx + 1) ? (1u << (2 * p)) : 0u;
+            smask |= ((int)hi16 >= a.rank_idx + 1) ? (2u << (2 * p)) : 0u;
         }
         const int lines_left = a.n_range - (r0 + ty * S);            // strips / columns past the edge of the map
         if (col >= a.n_doppler || lines_left <= 0) smask = 0u;
