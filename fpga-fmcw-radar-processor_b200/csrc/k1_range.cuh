@@ -137,11 +137,26 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
         }
     };
     fetch((int)blockIdx.x, 0);
+    // the raw samples of the NEXT tile are pulled into L2 while this one is transformed, so that the register
+    // prefetch above meets L2 latency instead of loaded-HBM latency (tiles are contiguous: tile_chirps * N samples)
+    auto l2_prefetch = [&](int t) {
+#ifndef RDP_EMU
+        if (t < n_tiles) {
+            const char* p = reinterpret_cast<const char*>(cube) + (long long)t * tile_chirps * N * (long long)sizeof(typename Raw::T);
+            const int bytes = tile_chirps * N * (int)sizeof(typename Raw::T);
+            for (int off = threadIdx.x * 128; off < bytes; off += THREADS * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+        }
+#else
+        (void)t;
+#endif
+    };
 
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int mp = t / tiles_per_map;
         const long long map = mp;
         const int c0 = (t - mp * tiles_per_map) * tile_chirps;
+        l2_prefetch(t + (int)gridDim.x);
         for (int it = 0; it < iters; ++it) {
             const int c = it * G + gid;
             const bool active = c < tile_chirps;
