@@ -168,7 +168,8 @@ struct K3Shape {
     static constexpr int NREF = WIN - (2 * GL + 1) * (2 * GC + 1);
     // phase 2: G lanes per survivor (32 / G survivors per warp pass), NQ window slots per lane
     static constexpr int G = WIN <= 160 ? 8 : (WIN <= 320 ? 16 : 32);
-    static constexpr int NQ = (WIN + G - 1) / G, NSLOT = NQ * G, NZ = NSLOT - NREF;
+    // (the slot table lists the reference cells only, padded to a multiple of G with slots that read a zero cell)
+    static constexpr int NQ = (NREF + G - 1) / G, NSLOT = NQ * G, NZ = NSLOT - NREF;
     static constexpr int TF_WORDS = (SROWS * SCOLS + 4 + 31) / 32 * 32;   // one raw stage (+ a cell that reads 0.0f), 128 B multiple
     static constexpr int ZERO_IDX = SROWS * SCOLS;
     static constexpr int TILE_BYTES = SROWS * SCOLS * 4;
@@ -276,11 +277,22 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         }
 #endif
     }
-    for (int sl = threadIdx.x; sl < Sh::NSLOT; sl += 256) {       // window slot -> reference cell, or the zero cell
-        const int dl = sl / (2 * HC + 1) - HL, dc = sl % (2 * HC + 1) - HC;
-        const bool ref = sl < Sh::WIN && !(dl >= -GL && dl <= GL && dc >= -GC && dc <= GC);
-        wtab[2 * sl] = ref ? 1 : 0;
-        wtab[2 * sl + 1] = ref ? dl * Sh::SCOLS + dc : Sh::ZERO_IDX;
+    for (int w = threadIdx.x; w < Sh::WIN + Sh::NZ; w += 256) {   // slot table: the reference cells in raster order, then padding
+        if (w < Sh::WIN) {
+            const int dl = w / (2 * HC + 1) - HL, dc = w % (2 * HC + 1) - HC;
+            if (!(dl >= -GL && dl <= GL && dc >= -GC && dc <= GC)) {
+                // guard cells in front of this one: whole guard rows above, part of its own row
+                int gb = (dl > GL ? 2 * GL + 1 : (dl > -GL ? dl + GL : 0)) * (2 * GC + 1);
+                if (dl >= -GL && dl <= GL) gb += dc > GC ? 2 * GC + 1 : 0;
+                const int sl = w - gb;
+                wtab[2 * sl] = 1;
+                wtab[2 * sl + 1] = dl * Sh::SCOLS + dc;
+            }
+        } else {
+            const int sl = Sh::NREF + (w - Sh::WIN);
+            wtab[2 * sl] = 0;
+            wtab[2 * sl + 1] = Sh::ZERO_IDX;
+        }
     }
     __syncthreads();
 #ifndef RDP_EMU
