@@ -299,9 +299,9 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     // TMA producer: the (tile + halo) box of tile `t` into raw stage `st`; coordinates may be negative /
     // past the edge -- the hardware zero-fills, which is exactly cfar_edges = ZERO
     const CUtensorMap* tmap_ptr = &tmap;                   // address of the __grid_constant__ parameter itself
-    auto issue = [=](long long t, int st) {
-        const long long mp = t / tiles_per_map;
-        const int rem = (int)(t % tiles_per_map);
+    auto issue = [=](int t, int st) {                     // tile indices fit 32 bits (checked by the host)
+        const int mp = t / tiles_per_map;
+        const int rem = t - mp * tiles_per_map;
         mbar_expect_tx(mbar + st, (uint32_t)Sh::TILE_BYTES);
         tma_load_3d(tf0 + st * Sh::TF_WORDS, tmap_ptr, mbar + st, (rem % tiles_c) * TCOLS - Sh::HCP, (rem / tiles_c) * Sh::TROWS - HL, (int)mp);
     };
@@ -309,11 +309,13 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
 #endif
 
     int iter = 0;
-    for (long long tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x, ++iter) {
+    const int n_tiles32 = (int)n_tiles;
+    for (int tile_id = blockIdx.x; tile_id < n_tiles32; tile_id += gridDim.x, ++iter) {
     const int stage = use_tma ? (iter & 1) : 0;
     float* tf = tf0 + stage * Sh::TF_WORDS;
     const long long map = tile_id / tiles_per_map;
-    const int tr = (int)(tile_id % tiles_per_map) / tiles_c, tc = (int)(tile_id % tiles_c);
+    const int in_map = tile_id - (int)map * tiles_per_map;
+    const int tr = in_map / tiles_c, tc = in_map - tr * tiles_c;
     const int r0 = tr * Sh::TROWS, c0 = tc * TCOLS;
     const float* m = rd_map + map * (long long)a.n_range * a.n_doppler;
 

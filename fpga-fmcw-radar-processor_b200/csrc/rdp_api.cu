@@ -468,6 +468,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
         const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
         const int tiles_c = (c.n_chirps + h->k3.tcols - 1) / h->k3.tcols;
         const long long n_tiles = maps * tiles_r * tiles_c;
+        if (n_tiles >= (1ll << 31)) return fail(h, RDP_E_CAPACITY, "CFAR stage: too many tiles in one launch; lower chunk_cpis");
         int use_tma = 0;
 #ifndef RDP_EMU
         // TMA stages the (tile + halo) box and zero-fills outside the map == cfar_edges ZERO; the flat-raster
