@@ -84,3 +84,19 @@ def test_product_loader_refuses_the_emulator():
         rdp.load_library(EMU)
     with pytest.raises(rdp.RdpError):
         rdp.load_library(os.path.join(ROOT, "does_not_exist.so"))
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/rdp.h is the drop-in boundary: a C caller (no C++, no CUDA headers) must be able to include it."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not installed")
+    src = tmp_path / "use_rdp.c"
+    src.write_text('#include "rdp.h"\n'
+                   "int main(void) { rdp_config c; rdp_det d; rdp_info i; rdp_scatter s; rdp_track t; rdp_tracker_config k;\n"
+                   "  (void)c; (void)d; (void)i; (void)s; (void)t; (void)k; return (int)sizeof(rdp_config) == 0; }\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                          "-c", str(src), "-o", str(tmp_path / "use_rdp.o")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
