@@ -183,6 +183,10 @@ def main():
         return run_reference(args, rank, world)
 
     import fpga_fmcw_radar_processor_b200 as rdp
+    from fpga_fmcw_radar_processor_b200 import affinity
+
+    # host placement before any page-locked buffer exists: this rank on the NUMA node of its GPU
+    numa = None if os.environ.get("RDP_NO_NUMA_BIND") else affinity.bind_to_gpu_numa_node(local_rank)
 
     dist = None
     if world > 1:
@@ -351,7 +355,8 @@ def main():
                            "unique_cpis": int(uniq.shape[0]), "chunk_cpis": info["chunk_cpis"],
                            "cfar": ("ref 8/8 guard 4/2" if CFAR_KW else "ref 4/4 guard 2/1") + " rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
                            "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),
-                           "device": info["device_name"], "cfar_tile_staging": "TMA" if core.info()["cfar_tma"] else "manual", "sharding": "CPIs dealt to ranks, no data-path collective"},
+                           "device": info["device_name"], "cfar_tile_staging": "TMA" if core.info()["cfar_tma"] else "manual", "sharding": "CPIs dealt to ranks, no data-path collective",
+                           "host_numa_binding": numa},
                 "clocks": clocks, "e2e": e2e, "streaming": streaming, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu,
                 "detections_per_cpi_mean": float(counts.mean()), "detections_per_cpi_max": int(counts.max()),

@@ -100,3 +100,13 @@ def test_two_rank_gloo_shard_and_merge():
     for f in ("cpi", "channel", "range", "doppler"):
         assert np.array_equal(merged[f], ref[f])
     assert np.array_equal(merged["mag"], ref["mag"])
+
+
+def test_affinity_helpers_are_safe_without_a_gpu():
+    """affinity.py is best-effort: parsing works, and with no GPU / sysfs entry it does nothing and returns None."""
+    from fpga_fmcw_radar_processor_b200 import affinity
+    assert affinity._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert affinity._cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert affinity.bind_to_gpu_numa_node(0) is None or isinstance(affinity.bind_to_gpu_numa_node(0), dict)
+    assert os.sched_getaffinity(0) <= before
