@@ -100,3 +100,12 @@ def test_header_is_plain_c99(tmp_path):
     out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
                           "-c", str(src), "-o", str(tmp_path / "use_rdp.o")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def test_c_example_builds_and_links():
+    """examples/rdp_frame.c -- the plain-C caller of the ABI -- compiles and links against librdp.so (make example)."""
+    import subprocess
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "fpga-fmcw-radar-processor_b200"), "example"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert os.access(os.path.join(ROOT, "examples", "rdp_frame"), os.X_OK)

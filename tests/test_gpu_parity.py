@@ -255,6 +255,28 @@ def test_sharded_cpi_multi_gpu():
     assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_c_example_matches_python_host(make_core, tmp_path):
+    """The plain-C caller (examples/rdp_frame.c): frame as text in, `r d mag` lines out == RadarCore.process."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "rdp_frame")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "fpga-fmcw-radar-processor_b200"), "example"])
+    nc, ns = 64, 256
+    cube, _ = st.synthetic_cube(1, 1, nc, ns, seed=5, sigma=25.0, n_targets=(2, 3))
+    frame = cube[0, 0].reshape(-1, 2)
+    np.savetxt(tmp_path / "frame.txt", frame, fmt="%d")
+    out = subprocess.run([exe, str(nc), str(ns), str(tmp_path / "frame.txt"), str(tmp_path / "dets.txt")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = np.loadtxt(tmp_path / "dets.txt", dtype=np.int64, ndmin=2)
+    with make_core(n_range=ns, n_doppler=nc, max_dets_per_cpi=1 << 16) as c:
+        dets = c.process(cube, want_map=False)[1]
+    assert len(got) == len(dets) > 0
+    assert np.array_equal(got[:, 0], dets["range"]) and np.array_equal(got[:, 1], dets["doppler"])
+    assert np.all(np.abs(got[:, 2] - dets["mag"]) <= 1.0)
+
+
 # ---- full-size, size-independent properties ---------------------------------------------------------
 def test_full_size_properties(make_core):
     """BASELINE config-3 shape (256 x 512 x 12 channels), 4 CPIs: determinism, exact x2 scaling
