@@ -319,7 +319,8 @@ class RadarCore:
                  detections DET_DTYPE in canonical (cpi, channel, range, doppler) order,
                  n_dets int32 [cpi] (as found; > max_dets_per_cpi means truncated), status uint32 [cpi]).
         The arrays are views of page-locked buffers owned by this object: valid until the next
-        process() call (copy them to keep them)."""
+        process() call or close() -- `.copy()` whatever must outlive that (touching a view after close()
+        reads freed memory).  process_cpi / process_batch below return copies."""
         cube = self._as_cube(cube)
         n_cpi = cube.shape[0]
         rd_map = self._out_buffer("map", (n_cpi, self.n_channels, self.n_range, self.n_doppler), np.float32) if want_map else None
