@@ -113,6 +113,7 @@ struct Dft<16> {
 template <int N, int E, int R_, int NS>
 struct FftPass {
     static constexpr int R = R_;
+    static constexpr int NSV = NS;        // product of the earlier radices
     static constexpr int T = N / E;       // threads per transform
     static constexpr int NB = E / R;      // butterflies per thread
     static constexpr int NTW = (NS > 1) ? NB * (R - 1) : 0;
@@ -162,9 +163,27 @@ struct FftPlan {
     static constexpr int TW1 = 0;
     static constexpr int TW2 = (R1 > 1 ? P1::NTW : 0);
     static constexpr int TW3 = TW2 + (R2 > 1 ? P2::NTW : 0);
-    // exchange buffer (per transform, per parity) in float2, padded one slot per 16
-    static __host__ __device__ constexpr int XPAD(int i) { return i + (i >> 4); }
-    static constexpr int XBUF = (NPASS > 1) ? (N + (N >> 4) + 1) : 0;
+    // Exchange buffer (per transform, per parity) in float2.  The layout is chosen per exchange from the pass that
+    // WRITES it, so that its stores are bank-conflict free (64-bit accesses go out per half-warp):
+    //  * first pass (NS = 1): lane j writes j R + r -> one pad slot per 16 elements;
+    //  * a pass with 2 <= NS < 16: lanes write runs of NS elements that start NS R apart; NS pad slots per NS R
+    //    elements put consecutive runs on consecutive banks (without them the runs of a half-warp collide:
+    //    measured 2-way conflicts on every store of the second exchange of the 512- and 256-point plans);
+    //  * NS >= 16: a run fills the half-warp, any layout works.
+    // The reading pass takes consecutive elements per lane, which stay consecutive within every padded block.
+    template <class PA>
+    static __host__ __device__ constexpr bool run_padded() {
+        return PA::NSV >= 2 && PA::NSV < 16 && (PA::NSV * PA::R) % 16 == 0;
+    }
+    template <class PA>
+    static __host__ __device__ constexpr int XPAD(int i) {
+        if constexpr (run_padded<PA>()) return i + (i / (PA::NSV * PA::R)) * PA::NSV;
+        else return i + (i >> 4);
+    }
+    template <class PA>
+    static __host__ __device__ constexpr int xextent() { return XPAD<PA>(N - 1) + 2; }
+    static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+    static constexpr int XBUF = (NPASS > 1) ? cmax(xextent<P0>(), cmax(R2 > 1 ? xextent<P1>() : 0, R3 > 1 ? xextent<P2>() : 0)) : 0;
     static constexpr int XBUFS = (1 + DB) * XBUF;        // float2 per transform group
     using LAST = typename std::conditional<(R3 > 1), P3, typename std::conditional<(R2 > 1), P2,
                  typename std::conditional<(R1 > 1), P1, P0>::type>::type>::type;
@@ -181,13 +200,13 @@ struct FftPlan {
         RDP_UNROLL
         for (int b = 0; b < PA::NB; ++b) {
             RDP_UNROLL
-            for (int r = 0; r < PA::R; ++r) xb[XPAD(PA::out_index(tid, b, r))] = v[b * PA::R + r];
+            for (int r = 0; r < PA::R; ++r) xb[XPAD<PA>(PA::out_index(tid, b, r))] = v[b * PA::R + r];
         }
         group_sync<GT>(gid);
         RDP_UNROLL
         for (int b = 0; b < PB::NB; ++b) {
             RDP_UNROLL
-            for (int r = 0; r < PB::R; ++r) v[b * PB::R + r] = xb[XPAD(PB::in_index(tid, b, r))];
+            for (int r = 0; r < PB::R; ++r) v[b * PB::R + r] = xb[XPAD<PA>(PB::in_index(tid, b, r))];
         }
     }
 
