@@ -141,9 +141,9 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
     // prefetch above meets L2 latency instead of loaded-HBM latency (tiles are contiguous: tile_chirps * N samples)
     auto l2_prefetch = [&](int t) {
 #ifndef RDP_EMU
-        if (t < n_tiles) {
+        const int bytes = tile_chirps * N * (int)sizeof(typename Raw::T);
+        if (t < n_tiles && bytes <= 64 * 1024) {               // measured: helps up to 64 KB tiles, hurts 128 KB ones
             const char* p = reinterpret_cast<const char*>(cube) + (long long)t * tile_chirps * N * (long long)sizeof(typename Raw::T);
-            const int bytes = tile_chirps * N * (int)sizeof(typename Raw::T);
             for (int off = threadIdx.x * 128; off < bytes; off += THREADS * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
         }
