@@ -8,27 +8,37 @@
 //     x_(k) < a         <=>   #{ref <  a} >= k + 1
 // (identities checked in tests/test_oracle_fixed.py).
 //
-// Phase 1 (every cell, the ALU-bound bulk): a CONSERVATIVE pre-filter against the most
-// permissive scale s1 (scale_override, or the smallest of SCALE_MIN/NOM/MAX).  The tile is
-// staged in shared memory twice: raw float32, and fl(v*s1) truncated to bfloat16 and duplicated
-// into both halves of a word.  Each thread owns S cells along range (one Doppler column), holds
-// their cut values rounded UP to bfloat16 packed two per register, and counts with one packed
-// compare per two (cell, reference) pairs (HSET2.BF16_V2 -> 0xFFFF masks, summed two at a time by
-// IADD3): measured 3.5x the rate of FSETP + predicated add on B200
-// (profiles/r1_mb_cmpacc_b200.txt).  ref_lo <= fl(v*s1) < cut <= cut_hi, so the packed count never
-// undercounts: no true detection is rejected.
-// In adaptive mode the pre-filter threshold is tightened per cell before it is rounded up: a cell can only
-// be detected with the scale the RTL would pick, so
+// A tile of the map (+ halo) is staged in shared memory twice: raw 32-bit words (TMA), and as
+// bfloat16 TRUNCATIONS packed two VERTICALLY adjacent cells per word (rows 2i, 2i+1 of one column),
+// column-major in two planes (even / odd columns) so that a thread reads the rows of a column with
+// 128-bit loads, conflict-free.  One packed compare (HSET2.BF16_V2 -> 0xFFFF masks, summed two at a
+// time by IADD3) then tests two reference cells against one threshold; references are rounded
+// DOWN and thresholds UP, so a packed count never undercounts.  Three phases, each a strict
+// (conservative) pre-filter of the next; only the last one decides:
+//
+// Phase 0 (every cell) -- SHARED threshold per strip, exploiting the window overlap.  A thread owns
+//   two adjacent strips of S = 8 cells along range.  A strip gets ONE threshold T_strip >= the
+//   pre-filter threshold of each of its cells (below), so `ref < T_strip` is one binary value per
+//   support cell, evaluated ONCE for the strip: (S + 2 HL) x (2 HC + 1) compares for 8 cells instead
+//   of 8 x N_REF, and the two strips of a thread share their loads.  The masks are accumulated per
+//   row pair; the window count of each cell (guard cells included: an upper bound) is a sliding sum
+//   of row counts.  count(T_strip) >= count(T_cell), so a strip none of whose cells reaches rank_idx + 1
+//   holds no detection.  In noise T_strip sits near 0.6 sigma: ~20 % of the references instead of the
+//   ~76 % needed -- whole strips are rejected with 15 packed compares per cell.
+// Phase 1 (surviving strips, compacted into a list so that warps stay dense) -- per-cell threshold:
+//   the conservative test against the most permissive scale s1.  In adaptive mode the threshold is
+//   tightened per cell before it is rounded up: a cell can only be detected with the scale the RTL
+//   would pick, so
 //     detection  =>  x_k < T = max(cut / SCALE_MAX, cut / SCALE_NOM, min(cut / SCALE_MIN, lo'))
-// where lo' >= lo = mean / 2 is an upper bound of the reference mean (the sum over the whole window, columns
-// widened to aligned groups of four, from a separable box filter over the staged tile).  SCALE_MIN is only
-// chosen when x_k < lo (:197), i.e. next to strong cells, so ordinary noise cells are tested against
-// cut / SCALE_NOM instead of cut / SCALE_MIN and almost never reach phase 2 (bench maps: survivors 5.0 % ->
-// 2.1 % of cells with 1.75 % true detections).  All bounds carry a 1e-3 relative margin, far above float32
-// rounding and far below the bfloat16 step; the decision itself stays with the exact phase 2.
-// Phase 2 (survivors only, ~0.5 % of noise cells + target cells): one warp per survivor decides
-// EXACTLY in float32 from the raw tile -- the s1 test, then (adaptive mode) float64 sum -> mean
-// -> scale 2/4/6 (:189-199) -> final test.  Decisions set bits in a per-tile bitmask.
+//   where lo' >= lo = mean / 2 is an upper bound of the reference mean (the sum over the whole window,
+//   columns widened to aligned groups of four, from a separable box filter over the staged tile).
+//   SCALE_MIN is only chosen when x_k < lo (:197), i.e. next to strong cells.  All bounds carry a 1e-3
+//   relative margin, far above float32 rounding and far below the bfloat16 step.
+// Phase 2 (surviving cells) -- the EXACT decision in float32 (or the RTL's integer arithmetic) from
+//   the raw tile: float64 sum -> mean -> scale 2/4/6 (:189-199) -> final count.
+// The packed pre-filters assume magnitudes >= 0.  A tile that holds a negative word (a signed map
+// handed to rdp_cfar_stage, or mag_mode = logpow below 0 dB) is decided cell by cell with the exact,
+// sign-safe arithmetic instead -- slow, but identical to the oracle.
 // K4 walks the bitmask of each CPI in (channel, range, doppler) order and writes the records, so
 // the list is canonical without a sort and truncation on overflow is deterministic.
 //   algorithmic HBM bytes / cell: 4 read (+4 if the dense RTL-style output is requested).
@@ -50,12 +60,16 @@ struct CfarArgs {
     int int_mode;                           // 1: the map holds unsigned integers and the decision is the bit-exact
                                             //    integer arithmetic of os_cfar_2d.vhd (DATA_WIDTH = 17)
     int is1, ismin, isnom, ismax;           // the scales as integers (int_mode)
-    // pre-filter threshold in the s1-scaled domain: Ts = max(cut * pf_a, min(cut * pf_b, window_sum * pf_c))
-    // (non-adaptive: pf_a = 1, pf_b = 0, i.e. Ts = cut)
+    // pre-filter threshold: T = max(cut * pf_a, min(cut * pf_b, window_sum * pf_c))
+    // (non-adaptive: pf_a = 1.001 / s1, pf_b = pf_c = 0)
     float pf_a, pf_b, pf_c;
 };
 
 // magnitude word -> float for the pre-filter; integers below 2^24 convert exactly
+template <bool INT_MODE>
+__device__ __forceinline__ float cfar_word_as_float(float raw) {
+    return INT_MODE ? (float)(uint32_t)__float_as_int(raw) : raw;
+}
 __device__ __forceinline__ float cfar_as_float(float raw, int int_mode) {
     return int_mode ? (float)(uint32_t)__float_as_int(raw) : raw;
 }
@@ -87,29 +101,27 @@ __device__ __forceinline__ uint32_t bf16x2_lt_mask(uint32_t a, uint32_t b) {
     return r;
 #endif
 }
-// pre-filter reference value as float (int_mode: the integer word; below 2^24 the conversion is exact).  The
-// scale s1 is NOT applied to the references: 1 / s1 (with a 1e-3 margin) is folded into the per-cell threshold.
-__device__ __forceinline__ float cfar_scaled(float raw, float s1, bool int_mode) {
-    (void)s1;
-    return int_mode ? (float)(uint32_t)__float_as_int(raw) : raw;
-}
-// bfloat16 truncation of v (>= 0), duplicated into both halves of a word
-__device__ __forceinline__ uint32_t bf16_dup(float v) {
+// two floats (>= 0) -> their bfloat16 truncations, `a` in the low half and `b` in the high half
+__device__ __forceinline__ uint32_t bf16_pack_down(float a, float b) {
 #ifdef RDP_EMU
-    const uint32_t lo = (uint32_t)__float_as_int(v) >> 16;
-    return lo | (lo << 16);
+    return ((uint32_t)__float_as_int(a) >> 16) | ((uint32_t)__float_as_int(b) & 0xffff0000u);
 #else
-    return __byte_perm((uint32_t)__float_as_int(v), 0u, 0x3232);
+    return __byte_perm((uint32_t)__float_as_int(a), (uint32_t)__float_as_int(b), 0x7632);
 #endif
 }
-// float (>= 0) -> bfloat16 bits rounded toward zero / toward +inf
-__device__ __forceinline__ uint32_t bf16_down(float v) { return (uint32_t)__float_as_int(v) >> 16; }
+// float (>= 0) -> bfloat16 bits rounded toward +inf
 __device__ __forceinline__ uint32_t bf16_up(float v) { return ((uint32_t)__float_as_int(v) + 0xffffu) >> 16; }
+// positive cuts so small that a threshold may fall into the bfloat16 subnormal range (pf_a >= 1e-6): one unsigned
+// compare on the bit pattern covers 0 < cut < 1e-30; such cells / strips skip the packed tests
+__device__ __forceinline__ bool cfar_tiny_cut(float cut) {
+    return (uint32_t)__float_as_int(cut) - 1u < 0x0da24260u - 1u;
+}
 
-// Exact decision for one cell by one warp from GLOBAL memory (generic kernel).
-template <int MAXQ>
-__device__ __forceinline__ bool cfar_exact_warp(const CfarArgs& a, const float* __restrict__ m,
-                                                int line, int col, float cut, int lane) {
+// Exact decision for one cell by one warp.  FETCH(dl, dc) returns the magnitude at that offset from the cell.
+// Sign-safe: nothing here assumes magnitudes >= 0 (a CUT equal to zero is never a detection: the RTL's output
+// word is the CUT itself and radar_core.vhd:415 keeps non-zero words only).
+template <int MAXQ, class FETCH>
+__device__ __forceinline__ bool cfar_exact_warp(const CfarArgs& a, FETCH fetch, float cut, int lane) {
     const int wc = 2 * a.half_c + 1;
     const int win = (2 * a.half_l + 1) * wc;
     float vals[MAXQ];
@@ -121,7 +133,7 @@ __device__ __forceinline__ bool cfar_exact_warp(const CfarArgs& a, const float* 
         const int dl = idx / wc - a.half_l, dc = idx % wc - a.half_c;
         const bool guard = (dl >= -a.guard_l && dl <= a.guard_l && dc >= -a.guard_c && dc <= a.guard_c);
         isref[q] = (idx < win) && !guard;
-        vals[q] = isref[q] ? cfar_fetch(m, line + dl, col + dc, a.n_range, a.n_doppler, a.raster) : 0.0f;
+        vals[q] = isref[q] ? fetch(dl, dc) : 0.0f;
         s += (double)vals[q];
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -145,42 +157,60 @@ __device__ __forceinline__ bool cfar_exact_warp(const CfarArgs& a, const float* 
     RDP_UNROLL
     for (int q = 0; q < MAXQ; ++q) c += (isref[q] && __fmul_rn(vals[q], scale) < cut) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
-    return c >= a.rank_idx + 1;                                    // cut > x_k * scale  (:213)
+    return c >= a.rank_idx + 1 && cut != 0.0f;                     // cut > x_k * scale  (:213), non-zero word
 }
 
 // ------------------------------------------------------------------------------------------
-// Tiled kernel, geometry compile-time.  CTA = 256 threads = TCOLS lanes along Doppler x
-// (256 / TCOLS) strips of S range lines.
+// Tiled kernel, geometry compile-time.  CTA = TR / 8 warps; tile = TR range lines x 64 Doppler
+// columns; warp = one band of 8 lines, lane = two adjacent columns.
 // ------------------------------------------------------------------------------------------
-template <int HL, int HC, int GL, int GC, int S, int TCOLS>
+template <int HL, int HC, int GL, int GC, int TR_, int NSTAGE_>
 struct K3Shape {
-    static constexpr int THREADS = 256;
-    static constexpr int TROWS = (THREADS / TCOLS) * S;
-    static constexpr int SROWS = TROWS + 2 * HL;
+    static constexpr int S = 8, TC = 64, TR = TR_, NSTAGE = NSTAGE_;
+    static constexpr int NBAND = TR / S, NWARP = NBAND, THREADS = 32 * NWARP;
     // TMA needs the box to START on a 16-byte boundary in the innermost dimension (an unaligned start
     // coordinate traps with "illegal instruction", tools/microbench/mb_tma_probe.cu), so the column halo is
-    // padded to a multiple of 4 floats on both sides: tile column c sits at shared column c + HCP
+    // padded to a multiple of 4 floats on both sides: tile column c sits at staged column c + HCP
     static constexpr int HCP = (HC + 3) / 4 * 4;
-    static constexpr int SCOLS = TCOLS + 2 * HCP;
+    static constexpr int SC = TC + 2 * HCP;                       // staged columns
+    static constexpr int SR = TR + 2 * HL;                        // staged rows (the TMA box)
+    static constexpr int SRP = (SR + 7) / 8 * 8;                  // ... padded with rows that stay zero
     static constexpr int WIN = (2 * HL + 1) * (2 * HC + 1);
     static constexpr int MAXQ = (WIN + 31) / 32;
-    static constexpr int TWORDS = (TCOLS + 31) / 32;              // bitmask words per tile row
+    static constexpr int TWORDS = TC / 32;                        // bitmask words per tile row
     static constexpr int NREF = WIN - (2 * GL + 1) * (2 * GC + 1);
+    // packed planes: word (col, i) = bf16 of staged rows (2i, 2i+1) of column col; plane = col & 1
+    static constexpr int NP = S / 2 + HL;                         // row pairs under one strip (its support)
+    static constexpr int NPL = (NP + 3) / 4;                      // 128-bit loads per column
+    static constexpr int PAIRS = SRP / 2;
+    static constexpr int PITCH_MIN = PAIRS > (NBAND - 1) * (S / 2) + 4 * NPL ? PAIRS : (NBAND - 1) * (S / 2) + 4 * NPL;
+    // consecutive lanes read consecutive columns of one plane with 128-bit loads: the 8 lanes of a quarter-warp
+    // cover all 32 banks iff the pitch is 4 mod 8 words
+    static constexpr int PITCH = PITCH_MIN + ((12 - PITCH_MIN % 8) % 8);
+    static constexpr int PLANE = (SC / 2) * PITCH;
+    // conversion pass: one item = 8 staged rows x 4 staged columns
+    static constexpr int NG = SC / 4, NQ8 = SRP / 8, NITEMS = NG * NQ8;
+    // window-sum bound of the adaptive pre-filter: aligned column groups of 4, NCOV groups cover any window
+    // (and the union of the windows of an even-aligned column pair)
+    static constexpr int NCOV = (2 * HC + 7) / 4;
     // phase 2: G lanes per survivor (32 / G survivors per warp pass), NQ window slots per lane
     static constexpr int G = WIN <= 160 ? 8 : (WIN <= 320 ? 16 : 32);
     // (the slot table lists the reference cells only, padded to a multiple of G with slots that read a zero cell)
     static constexpr int NQ = (NREF + G - 1) / G, NSLOT = NQ * G, NZ = NSLOT - NREF;
-    static constexpr int TF_WORDS = (SROWS * SCOLS + 4 + 31) / 32 * 32;   // one raw stage (+ a cell that reads 0.0f), 128 B multiple
-    static constexpr int ZERO_IDX = SROWS * SCOLS;
-    static constexpr int TILE_BYTES = SROWS * SCOLS * 4;
-    // window-sum bound of the adaptive pre-filter: column groups of 4, NCOV groups cover any window
-    static constexpr int NCG = SCOLS / 4, NCOV = (2 * HC + 7) / 4;
-    static constexpr int SURV_WORDS = TROWS * TCOLS / 2;
-    static_assert(TROWS * TCOLS <= 65536, "survivor codes are 16-bit");
-    static_assert(4 * NCOV >= 2 * HC + 1 + 3, "NCOV groups cover the window at any alignment");
+    static constexpr int ZERO_IDX = SRP * SC;
+    static constexpr int TF_WORDS = (SRP * SC + 4 + 31) / 32 * 32;    // one raw stage (+ a cell that reads 0.0f), 128 B multiple
+    static constexpr int TILE_BYTES = SR * SC * 4;
+    static constexpr int N_STRIPS = NBAND * TC;
+    static_assert(TR % S == 0 && TR * TC <= 65536 && (SC % 4) == 0 && (PITCH % 8) == 4 && PITCH % 4 == 0, "tile geometry");
+    static_assert(4 * NCOV >= 2 * HC + 1 + 3 && 4 * NCOV >= 2 * HC + 2 + (HC % 2 ? 3 : 2), "NCOV groups cover the window at any alignment");
     static constexpr size_t smem_bytes() {
-        return sizeof(float) * (2 * TF_WORDS + SROWS * SCOLS) +
-               sizeof(int) * (SURV_WORDS + SROWS * NCG + TROWS * TWORDS + 4 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
+        return sizeof(float) * ((size_t)NSTAGE * TF_WORDS + SRP * NG) + sizeof(uint32_t) * (2 * PLANE + TR * TWORDS) +
+               sizeof(unsigned short) * (N_STRIPS + TR * TC) + sizeof(int) * (8 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
+    }
+    static constexpr int occupancy_hint() {                        // CTAs per SM the shared memory allows (<= 2048 threads)
+        int n = (int)((227 * 1024) / (smem_bytes() + 1024));
+        if (n > 2048 / THREADS) n = 2048 / THREADS;
+        return n < 1 ? 1 : n;
     }
 };
 
@@ -216,59 +246,88 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
 }
 #endif
 
-// one packed compare for cells (2p, 2p+1) of the strip against tile row lr, if either is a reference
-template <int HL, int GL, bool GUARD_COL, int P, int LR>
-__device__ __forceinline__ void k3_pair(uint32_t v, const uint32_t (&cb)[4], const uint32_t (&cl)[4],
-                                        const uint32_t (&ch)[4], uint32_t (&acc)[4]) {
-    constexpr int dl0 = LR - 2 * P - HL, dl1 = dl0 - 1;            // line offset of row LR from cell 2p, 2p+1
-    constexpr bool in0 = dl0 >= -HL && dl0 <= HL && !(GUARD_COL && dl0 >= -GL && dl0 <= GL);
-    constexpr bool in1 = dl1 >= -HL && dl1 <= HL && !(GUARD_COL && dl1 >= -GL && dl1 <= GL);
-    if (in0 && in1) acc[P] -= bf16x2_lt_mask(v, cb[P]);
-    else if (in0) acc[P] -= bf16x2_lt_mask(v, cl[P]);
-    else if (in1) acc[P] -= bf16x2_lt_mask(v, ch[P]);
+// pf_c x the sums of the S vertical windows of a strip: wsum[j] = pf_c * sum_{k = j .. j + 2 HL} x[k].  Additions only
+// (a sliding subtraction could cancel a huge line against the rest and fall BELOW the true sum).
+template <int HL, int S>
+__device__ __forceinline__ void k3_window_sums(const float (&x)[S + 2 * HL], float pf_c, float (&wsum)[S]) {
+    if constexpr (2 * HL >= S - 1) {
+        float common = x[S - 1];                                   // lines S-1 .. 2 HL belong to every window
+        RDP_UNROLL
+        for (int k = S; k <= 2 * HL; ++k) common += x[k];
+        common *= pf_c;
+        float part = 0.0f;
+        wsum[S - 1] = common;
+        RDP_UNROLL
+        for (int j = S - 2; j >= 0; --j) { part += x[j]; wsum[j] = fmaf(part, pf_c, common); }
+        part = 0.0f;
+        RDP_UNROLL
+        for (int j = 1; j < S; ++j) { part += x[2 * HL + j]; wsum[j] = fmaf(part, pf_c, wsum[j]); }
+    } else {
+        RDP_UNROLL
+        for (int j = 0; j < S; ++j) {
+            wsum[j] = 0.0f;
+            RDP_UNROLL
+            for (int k = 0; k <= 2 * HL; ++k) wsum[j] += x[j + k];
+            wsum[j] *= pf_c;
+        }
+    }
 }
 
-template <int HL, int GL, bool GUARD_COL, int LR, int NROWS>
-struct K3Rows {
-    static __device__ __forceinline__ void run(const uint32_t* __restrict__ tp, int pitch, const uint32_t (&cb)[4],
-                                               const uint32_t (&cl)[4], const uint32_t (&ch)[4], uint32_t (&acc)[4]) {
-        const uint32_t v = tp[LR * pitch];
-        k3_pair<HL, GL, GUARD_COL, 0, LR>(v, cb, cl, ch, acc);
-        k3_pair<HL, GL, GUARD_COL, 1, LR>(v, cb, cl, ch, acc);
-        k3_pair<HL, GL, GUARD_COL, 2, LR>(v, cb, cl, ch, acc);
-        k3_pair<HL, GL, GUARD_COL, 3, LR>(v, cb, cl, ch, acc);
-        K3Rows<HL, GL, GUARD_COL, LR + 1, NROWS>::run(tp, pitch, cb, cl, ch, acc);
-    }
-};
-template <int HL, int GL, bool GUARD_COL, int NROWS>
-struct K3Rows<HL, GL, GUARD_COL, NROWS, NROWS> {
-    static __device__ __forceinline__ void run(const uint32_t* __restrict__, int, const uint32_t (&)[4],
-                                               const uint32_t (&)[4], const uint32_t (&)[4], uint32_t (&)[4]) {}
-};
+// Packed counters: every packed compare yields 0xFFFF per true half and is SUBTRACTED from a 32-bit accumulator, so
+// the low half counts its own hits and the high half holds (high hits - low hits) mod 2^16 (the borrow of the low
+// half).  Sums of accumulators keep that form.
+__device__ __forceinline__ uint32_t k3_lo_count(uint32_t p) { return p & 0xffffu; }
+__device__ __forceinline__ uint32_t k3_hi_count(uint32_t p) { return ((p >> 16) + p) & 0xffffu; }
 
-template <int HL, int HC, int GL, int GC, int S, int TCOLS, bool INT_MODE>
-__global__ void __launch_bounds__(256)
+// Phase 0 verdict of one strip from its per-row-pair packed counters P[i] (low half: row 2i, high half: row 2i+1):
+// does any of the 8 cells reach `need` references below the strip threshold?  Cells 2m and 2m+1 share the rows
+// 2m .. 2m + 2 HL + 1 = pairs m .. m + HL; cell 2m lacks the last of them, cell 2m+1 the first.
+template <int HL, int NP>
+__device__ __forceinline__ bool k3_strip_reaches(const uint32_t (&P)[NP], int need) {
+    uint32_t R = 0u;
+    RDP_UNROLL
+    for (int i = 0; i <= HL; ++i) R += P[i];
+    bool f = false;
+    RDP_UNROLL
+    for (int m = 0; m < 4; ++m) {
+        const uint32_t t = k3_lo_count(R) + k3_hi_count(R);
+        const uint32_t hi_last = k3_hi_count(P[m + HL]), lo_first = k3_lo_count(P[m]);
+        f = f || (int)(t - (hi_last < lo_first ? hi_last : lo_first)) >= need;
+        if (m < 3) R = R - P[m] + P[m + HL + 1];
+    }
+    return f;
+}
+
+template <int HL, int HC, int GL, int GC, int TR, int NSTAGE, bool INT_MODE>
+__global__ void __launch_bounds__((K3Shape<HL, HC, GL, GC, TR, NSTAGE>::THREADS), (K3Shape<HL, HC, GL, GC, TR, NSTAGE>::occupancy_hint()))
 k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, uint32_t* __restrict__ det_bits,
                CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
                const RDP_GRID_CONSTANT CUtensorMap tmap) {
-    static_assert(S == 8, "the strip is four packed pairs");
-    using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
+    using Sh = K3Shape<HL, HC, GL, GC, TR, NSTAGE>;
+    constexpr int S = Sh::S, TC = Sh::TC, SC = Sh::SC, SR = Sh::SR, SRP = Sh::SRP, HCP = Sh::HCP, NG = Sh::NG;
+    constexpr int NP = Sh::NP, NPL = Sh::NPL, PITCH = Sh::PITCH, PLANE = Sh::PLANE, THREADS = Sh::THREADS, NWARP = Sh::NWARP;
     RDP_DYN_SMEM(smem_raw);
-    // 128-byte aligned carve-up: [2 raw stages][packed tile][survivors][group sums][bitmask][counter][window table][mbarriers]
+    // 128-byte aligned carve-up: [raw stages][packed planes][cover sums][bitmask][counters][window table][strip list][survivors][mbarriers]
     unsigned char* smem_al = smem_raw + ((128 - ((uintptr_t)smem_raw & 127)) & 127);
-    float* tf0 = reinterpret_cast<float*>(smem_al);                            // raw magnitudes, two stages
-    uint32_t* th = reinterpret_cast<uint32_t*>(tf0 + 2 * Sh::TF_WORDS);        // bf16x2 (lo, lo) of fl(v*s1)
-    unsigned short* surv = reinterpret_cast<unsigned short*>(th + Sh::SROWS * Sh::SCOLS);   // 16-bit survivor codes
-    float* grp = reinterpret_cast<float*>(surv) + Sh::SURV_WORDS;              // [SROWS][NCG] sums of 4 NCOV columns
-    uint32_t* bits = reinterpret_cast<uint32_t*>(grp + Sh::SROWS * Sh::NCG);
-    int* n_surv = reinterpret_cast<int*>(bits + Sh::TROWS * Sh::TWORDS);
-    int* wtab = n_surv + 4;                                                    // [NSLOT][2]: tf index = ctr * mul + add
+    float* tf0 = reinterpret_cast<float*>(smem_al);                             // raw magnitudes
+    uint32_t* planes = reinterpret_cast<uint32_t*>(tf0 + NSTAGE * Sh::TF_WORDS);  // [2][SC / 2][PITCH] bf16 row pairs
+    float* cov = reinterpret_cast<float*>(planes + 2 * PLANE);                  // [SRP][NG] sums of the 4 NCOV columns from group g on
+    uint32_t* bits = reinterpret_cast<uint32_t*>(cov + SRP * NG);               // [TR][TWORDS]
+    int* ctr = reinterpret_cast<int*>(bits + TR * Sh::TWORDS);                  // 0: strips listed, 1: survivors listed, 2 / 3: tile holds a negative word (by iteration parity)
+    int* wtab = ctr + 8;                                                        // [NSLOT][2]: tf index = ctr * mul + add
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wtab + 2 * Sh::NSLOT);
+    unsigned short* strips = reinterpret_cast<unsigned short*>(mbar + 2);       // band * 64 + column
+    unsigned short* surv = strips + Sh::N_STRIPS;                               // tile line * 64 + column
     const int tiles_per_map = tiles_r * tiles_c;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int need = a.rank_idx + 1;
 
+    // rows SR .. SRP-1 of every raw stage and its zero cell are never written again
+    for (int st = 0; st < NSTAGE; ++st)
+        for (int i = SR * SC + threadIdx.x; i < Sh::TF_WORDS; i += THREADS) tf0[st * Sh::TF_WORDS + i] = 0.0f;
+    for (int i = threadIdx.x; i < TR * Sh::TWORDS; i += THREADS) bits[i] = 0u;
     if (threadIdx.x == 0) {
-        tf0[Sh::ZERO_IDX] = 0.0f;
-        tf0[Sh::TF_WORDS + Sh::ZERO_IDX] = 0.0f;
+        ctr[0] = 0; ctr[1] = 0; ctr[2] = 0; ctr[3] = 0;
 #ifndef RDP_EMU
         if (use_tma) {
             mbar_init(mbar, 1);
@@ -277,7 +336,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         }
 #endif
     }
-    for (int w = threadIdx.x; w < Sh::WIN + Sh::NZ; w += 256) {   // slot table: the reference cells in raster order, then padding
+    for (int w = threadIdx.x; w < Sh::WIN + Sh::NZ; w += THREADS) {   // slot table: the reference cells in raster order, then padding
         if (w < Sh::WIN) {
             const int dl = w / (2 * HC + 1) - HL, dc = w % (2 * HC + 1) - HC;
             if (!(dl >= -GL && dl <= GL && dc >= -GC && dc <= GC)) {
@@ -286,7 +345,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                 if (dl >= -GL && dl <= GL) gb += dc > GC ? 2 * GC + 1 : 0;
                 const int sl = w - gb;
                 wtab[2 * sl] = 1;
-                wtab[2 * sl + 1] = dl * Sh::SCOLS + dc;
+                wtab[2 * sl + 1] = dl * SC + dc;
             }
         } else {
             const int sl = Sh::NREF + (w - Sh::WIN);
@@ -303,7 +362,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         const int mp = t / tiles_per_map;
         const int rem = t - mp * tiles_per_map;
         mbar_expect_tx(mbar + st, (uint32_t)Sh::TILE_BYTES);
-        tma_load_3d(tf0 + st * Sh::TF_WORDS, tmap_ptr, mbar + st, (rem % tiles_c) * TCOLS - Sh::HCP, (rem / tiles_c) * Sh::TROWS - HL, (int)mp);
+        tma_load_3d(tf0 + st * Sh::TF_WORDS, tmap_ptr, mbar + st, (rem % tiles_c) * TC - HCP, (rem / tiles_c) * TR - HL, (int)mp);
     };
     if (use_tma && threadIdx.x == 0 && (long long)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
 #endif
@@ -311,80 +370,34 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     int iter = 0;
     const int n_tiles32 = (int)n_tiles;
     for (int tile_id = blockIdx.x; tile_id < n_tiles32; tile_id += gridDim.x, ++iter) {
-    const int stage = use_tma ? (iter & 1) : 0;
+    const int stage = (use_tma && NSTAGE == 2) ? (iter & 1) : 0;
     float* tf = tf0 + stage * Sh::TF_WORDS;
     const long long map = tile_id / tiles_per_map;
     const int in_map = tile_id - (int)map * tiles_per_map;
     const int tr = in_map / tiles_c, tc = in_map - tr * tiles_c;
-    const int r0 = tr * Sh::TROWS, c0 = tc * TCOLS;
+    const int r0 = tr * TR, c0 = tc * TC;
     const float* m = rd_map + map * (long long)a.n_range * a.n_doppler;
+    const long long out_base = map * (long long)a.n_range * a.n_doppler;
 
-    if (threadIdx.x == 0) *n_surv = 0;
-    for (int i = threadIdx.x; i < Sh::TROWS * Sh::TWORDS; i += 256) bits[i] = 0u;
 #ifndef RDP_EMU
     if (use_tma) {
-        // prefetch the next tile into the other stage (its previous readers finished before the barrier that
-        // ended the previous iteration), then wait for this tile's bytes
-        if (threadIdx.x == 0 && tile_id + gridDim.x < n_tiles) issue(tile_id + gridDim.x, stage ^ 1);
-        mbar_wait(mbar + stage, (uint32_t)((iter >> 1) & 1));
-        // raw words -> packed bf16x2 (lo, lo), four cells per thread per step (128-bit shared-memory accesses)
-        // int_mode: the product is rounded toward zero so that ref_lo never exceeds the exact integer product
-        const float4* tf4 = reinterpret_cast<const float4*>(tf);
-        uint4* th4 = reinterpret_cast<uint4*>(th);
-        if (a.adaptive) {
-            // ... and, for the adaptive pre-filter bound, grp[row][g] = sum of the 4 NCOV columns from group g on
-            // (each warp steps by 32 - (NCOV - 1) chunks so that the neighbours it needs sit in its own lanes)
-            constexpr int OV = Sh::NCOV - 1, ADV = 32 - OV, NCH = Sh::SROWS * Sh::SCOLS / 4;
-            const int lane_s = threadIdx.x % 32;
-            for (int base = (threadIdx.x / 32) * ADV; base < NCH; base += 8 * ADV) {
-                const int i = base + lane_s;
-                float g = 0.0f;
-                if (i < NCH) {
-                    const float4 r = tf4[i];
-                    if (lane_s < ADV) {
-                        uint4 o;
-                        o.x = bf16_dup(cfar_scaled(r.x, a.s1, INT_MODE));
-                        o.y = bf16_dup(cfar_scaled(r.y, a.s1, INT_MODE));
-                        o.z = bf16_dup(cfar_scaled(r.z, a.s1, INT_MODE));
-                        o.w = bf16_dup(cfar_scaled(r.w, a.s1, INT_MODE));
-                        th4[i] = o;
-                    }
-                    g = (cfar_as_float(r.x, INT_MODE) + cfar_as_float(r.y, INT_MODE)) +
-                        (cfar_as_float(r.z, INT_MODE) + cfar_as_float(r.w, INT_MODE));
-                }
-                float cover = g;
-                const int cg = i % Sh::NCG;                       // groups past the end of the row count as 0
-                RDP_UNROLL
-                for (int k = 1; k <= OV; ++k) {
-                    const float nb = __shfl_down_sync(0xffffffffu, g, k);
-                    cover += cg + k < Sh::NCG ? nb : 0.0f;
-                }
-                if (lane_s < ADV && i < NCH) grp[i] = cover;
-            }
-        } else {
-            for (int i = threadIdx.x; i < Sh::SROWS * Sh::SCOLS / 4; i += 256) {
-                const float4 r = tf4[i];
-                uint4 o;
-                o.x = bf16_dup(cfar_scaled(r.x, a.s1, INT_MODE));
-                o.y = bf16_dup(cfar_scaled(r.y, a.s1, INT_MODE));
-                o.z = bf16_dup(cfar_scaled(r.z, a.s1, INT_MODE));
-                o.w = bf16_dup(cfar_scaled(r.w, a.s1, INT_MODE));
-                th4[i] = o;
-            }
-        }
+        // two stages: the next tile is fetched into the other stage (its readers finished before the barrier that
+        // ended the previous iteration) while this one is processed; one stage: it was issued at the end of the
+        // previous iteration and other CTAs of the SM cover the latency
+        if (NSTAGE == 2 && threadIdx.x == 0 && tile_id + (int)gridDim.x < n_tiles32) issue(tile_id + gridDim.x, stage ^ 1);
+        mbar_wait(mbar + stage, (uint32_t)((NSTAGE == 2 ? (iter >> 1) : iter) & 1));
     } else
 #endif
-    {   // tile + halo, one warp per tile row (coalesced, no per-element index arithmetic)
-        const int lw = threadIdx.x / 32, ll = threadIdx.x % 32;
-        for (int lr = lw; lr < Sh::SROWS; lr += 8) {
+    {   // tile + halo, one warp per staged row (coalesced, no per-element index arithmetic)
+        for (int lr = warp; lr < SR; lr += NWARP) {
             const int line = r0 - HL + lr;
             const bool row_ok = a.raster || (line >= 0 && line < a.n_range);
             const long long row_base = (long long)line * a.n_doppler;
             RDP_UNROLL
-            for (int k = 0; k < (Sh::SCOLS + 31) / 32; ++k) {
-                const int lc = ll + 32 * k;
-                if (lc < Sh::SCOLS) {
-                    const int c = c0 - Sh::HCP + lc;
+            for (int k = 0; k < (SC + 31) / 32; ++k) {
+                const int lc = lane + 32 * k;
+                if (lc < SC) {
+                    const int c = c0 - HCP + lc;
                     float v = 0.0f;
                     if (a.raster) {
                         const long long flat = row_base + c;
@@ -392,132 +405,214 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                     } else if (row_ok && c >= 0 && c < a.n_doppler) {
                         v = __ldg(m + row_base + c);
                     }
-                    tf[lr * Sh::SCOLS + lc] = v;
-                    th[lr * Sh::SCOLS + lc] = bf16_dup(cfar_scaled(v, a.s1, INT_MODE));
+                    tf[lr * SC + lc] = v;
                 }
             }
         }
-        if (a.adaptive) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < Sh::SROWS * Sh::NCG; i += 256) {
-                float cover = 0.0f;
-                RDP_UNROLL
-                for (int k = 0; k < 4 * Sh::NCOV; ++k)
-                    if (4 * (i % Sh::NCG) + k < Sh::SCOLS) cover += cfar_as_float(tf[4 * i + k], INT_MODE);
-                grp[i] = cover;
+        __syncthreads();
+    }
+
+    // ---- conversion: raw words -> packed bf16 row pairs (two planes), column-group cover sums, sign check --------
+    {
+        constexpr int OV = Sh::NCOV - 1, ADV = 32 - OV;
+        static_assert(ADV >= 8, "cover shuffles");
+        const float4* tf4 = reinterpret_cast<const float4*>(tf);
+        uint32_t neg = 0u;
+        for (int base = warp * ADV; base < Sh::NITEMS; base += NWARP * ADV) {
+            const int it = base + lane;
+            const bool ok = it < Sh::NITEMS;
+            const int q = ok ? it / NG : 0, g = ok ? it - q * NG : 0;
+            float gs[8];
+            uint32_t wd[4][4];                                      // [column of the group][row pair]
+            RDP_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                const float4 ra = tf4[((8 * q + 2 * i) * SC + 4 * g) >> 2];
+                const float4 rb = tf4[((8 * q + 2 * i + 1) * SC + 4 * g) >> 2];
+                if (!INT_MODE) {
+                    neg |= (uint32_t)__float_as_int(ra.x) | (uint32_t)__float_as_int(ra.y) | (uint32_t)__float_as_int(ra.z) | (uint32_t)__float_as_int(ra.w);
+                    neg |= (uint32_t)__float_as_int(rb.x) | (uint32_t)__float_as_int(rb.y) | (uint32_t)__float_as_int(rb.z) | (uint32_t)__float_as_int(rb.w);
+                }
+                const float ax = cfar_word_as_float<INT_MODE>(ra.x), ay = cfar_word_as_float<INT_MODE>(ra.y);
+                const float az = cfar_word_as_float<INT_MODE>(ra.z), aw = cfar_word_as_float<INT_MODE>(ra.w);
+                const float bx = cfar_word_as_float<INT_MODE>(rb.x), by = cfar_word_as_float<INT_MODE>(rb.y);
+                const float bz = cfar_word_as_float<INT_MODE>(rb.z), bw = cfar_word_as_float<INT_MODE>(rb.w);
+                wd[0][i] = bf16_pack_down(ax, bx);
+                wd[1][i] = bf16_pack_down(ay, by);
+                wd[2][i] = bf16_pack_down(az, bz);
+                wd[3][i] = bf16_pack_down(aw, bw);
+                gs[2 * i] = (ax + ay) + (az + aw);
+                gs[2 * i + 1] = (bx + by) + (bz + bw);
             }
+            const bool mine = ok && lane < ADV;
+            if (mine) {
+                RDP_UNROLL
+                for (int c = 0; c < 4; ++c) {
+                    uint4 o;
+                    o.x = wd[c][0]; o.y = wd[c][1]; o.z = wd[c][2]; o.w = wd[c][3];
+                    *reinterpret_cast<uint4*>(planes + (c & 1) * PLANE + (2 * g + (c >> 1)) * PITCH + 4 * q) = o;
+                }
+            }
+            if (a.adaptive) {
+                // cov[row][g] = sum of the 4 NCOV columns from group g on (groups past the end of the row count as 0);
+                // each warp steps by 32 - (NCOV - 1) items so that the neighbours it needs sit in its own lanes
+                RDP_UNROLL
+                for (int k = 0; k < 8; ++k) {
+                    float cover = gs[k];
+                    RDP_UNROLL
+                    for (int d = 1; d <= OV; ++d) {
+                        const float nb = __shfl_down_sync(0xffffffffu, gs[k], d);
+                        cover += g + d < NG ? nb : 0.0f;
+                    }
+                    if (mine) cov[(8 * q + k) * NG + g] = cover;
+                }
+            }
+        }
+        if (!INT_MODE) {
+            if (__any_sync(0xffffffffu, (int)(neg >> 31)) && lane == 0) ctr[2 + (iter & 1)] = 1;
+        }
+    }
+    __syncthreads();
+    const bool signed_tile = !INT_MODE && ctr[2 + (iter & 1)] != 0;   // (reset after the tile; the next tile raises the other flag)
+
+    if (!signed_tile) {
+    // ---- phase 0: one shared threshold per strip ------------------------------------------------------------
+    {
+        const int b = warp;                                        // band: tile lines 8 b .. 8 b + 7, staged rows 8 b .. 8 b + 7 + 2 HL
+        const int s0 = 2 * lane + HCP;                             // staged column of the first of this lane's two columns
+        float cm0 = 0.0f, cm1 = 0.0f;                              // largest cut of either strip
+        RDP_UNROLL
+        for (int j = 0; j < S; ++j) {
+            const float2 c2 = *reinterpret_cast<const float2*>(tf + (S * b + HL + j) * SC + s0);
+            cm0 = fmaxf(cm0, cfar_word_as_float<INT_MODE>(c2.x));
+            cm1 = fmaxf(cm1, cfar_word_as_float<INT_MODE>(c2.y));
+        }
+        float lo_b = 0.0f;                                         // pf_c x the largest window-sum bound of the strip's cells
+        if (a.adaptive) {
+            const float* gp = cov + (S * b) * NG + ((s0 - HC) >> 2);
+            float x[S + 2 * HL];
+            RDP_UNROLL
+            for (int k = 0; k < S + 2 * HL; ++k) x[k] = gp[k * NG];
+            float wsum[S];
+            k3_window_sums<HL, S>(x, a.pf_c, wsum);
+            lo_b = wsum[0];
+            RDP_UNROLL
+            for (int j = 1; j < S; ++j) lo_b = fmaxf(lo_b, wsum[j]);
+        }
+        const float t0 = fmaxf(cm0 * a.pf_a, fminf(cm0 * a.pf_b, lo_b));
+        const float t1 = fmaxf(cm1 * a.pf_a, fminf(cm1 * a.pf_b, lo_b));
+        const uint32_t h0 = bf16_up(t0), h1 = bf16_up(t1);
+        const uint32_t td0 = h0 | (h0 << 16), td1 = h1 | (h1 << 16);
+        uint32_t acc0[NP], acc1[NP];
+        RDP_UNROLL
+        for (int i = 0; i < NP; ++i) { acc0[i] = 0u; acc1[i] = 0u; }
+        const uint32_t* pl = planes + (S / 2) * b + lane * PITCH;
+        RDP_UNROLL
+        for (int k = 0; k <= 2 * HC + 1; ++k) {                    // staged column s0 - HC + k: parity and plane position are compile-time
+            const uint4* src = reinterpret_cast<const uint4*>(pl + ((HC + k) & 1) * PLANE + ((HCP - HC + k) >> 1) * PITCH);
+            uint32_t w[4 * NPL];
+            RDP_UNROLL
+            for (int v = 0; v < NPL; ++v) {
+                const uint4 u = src[v];
+                w[4 * v] = u.x; w[4 * v + 1] = u.y; w[4 * v + 2] = u.z; w[4 * v + 3] = u.w;
+            }
+            if (k <= 2 * HC) {
+                RDP_UNROLL
+                for (int i = 0; i < NP; ++i) acc0[i] -= bf16x2_lt_mask(w[i], td0);
+            }
+            if (k >= 1) {
+                RDP_UNROLL
+                for (int i = 0; i < NP; ++i) acc1[i] -= bf16x2_lt_mask(w[i], td1);
+            }
+        }
+        const bool f0 = k3_strip_reaches<HL, NP>(acc0, need) || cfar_tiny_cut(cm0);
+        const bool f1 = k3_strip_reaches<HL, NP>(acc1, need) || cfar_tiny_cut(cm1);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+        const int n0 = __popc(b0), n1 = __popc(b1);
+        if (n0 + n1) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ctr, n0 + n1);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t below = (1u << lane) - 1u;
+            if (f0) strips[base + __popc(b0 & below)] = (unsigned short)(b * TC + 2 * lane);
+            if (f1) strips[base + n0 + __popc(b1 & below)] = (unsigned short)(b * TC + 2 * lane + 1);
+        }
+        if (cfar_out && c0 + 2 * lane < a.n_doppler) {             // dense output: zero everywhere, phase 2 writes the detections
+            RDP_UNROLL
+            for (int j = 0; j < S; ++j)
+                if (r0 + S * b + j < a.n_range)
+                    *reinterpret_cast<float2*>(cfar_out + out_base + (long long)(r0 + S * b + j) * a.n_doppler + c0 + 2 * lane) = make_float2(0.0f, 0.0f);
         }
     }
     __syncthreads();
 
-    // ---- phase 1: conservative packed pre-filter ---------------------------------------------------
-    const int tx = threadIdx.x % TCOLS, ty = threadIdx.x / TCOLS;
-    const int col = c0 + tx;
-    uint32_t cb[4], cl[4], ch[4], acc[4];
-    uint32_t fmask = 0u;                                          // bit j: cell j of the strip goes to the exact phase regardless
-    float wsum[S];                                                // adaptive: pf_c x bound of the window sum of each cell
-    if (a.adaptive) {
-        // vertical pass of the box filter in registers: wsum[j] = sum_{k = j .. j + 2 HL} x[k], additions only
-        const float* gp = grp + (ty * S) * Sh::NCG + ((tx + Sh::HCP - HC) >> 2);
-        float x[S + 2 * HL];
-        RDP_UNROLL
-        for (int k = 0; k < S + 2 * HL; ++k) x[k] = gp[k * Sh::NCG];
-        if constexpr (2 * HL >= S - 1) {
-            float common = x[S - 1];                              // lines S-1 .. 2 HL belong to every window
-            RDP_UNROLL
-            for (int k = S; k <= 2 * HL; ++k) common += x[k];
-            common *= a.pf_c;                                     // wsum comes out already times pf_c
-            float part = 0.0f;
-            wsum[S - 1] = common;
-            RDP_UNROLL
-            for (int j = S - 2; j >= 0; --j) { part += x[j]; wsum[j] = fmaf(part, a.pf_c, common); }
-            part = 0.0f;
-            RDP_UNROLL
-            for (int j = 1; j < S; ++j) { part += x[2 * HL + j]; wsum[j] = fmaf(part, a.pf_c, wsum[j]); }
-        } else {
+    // ---- phase 1: surviving strips, per-cell thresholds -----------------------------------------------------
+    {
+        const int n_strips = ctr[0];
+        for (int idx = threadIdx.x; idx < n_strips; idx += THREADS) {
+            const int code = strips[idx];
+            const int b = code / TC, tx = code % TC;
+            const int s = tx + HCP;                                 // staged column of the strip
+            float wsum[S];
+            if (a.adaptive) {
+                // vertical pass of the box filter in registers: wsum[j] = pf_c x sum_{k = j .. j + 2 HL} x[k], additions only
+                const float* gp = cov + (S * b) * NG + ((s - HC) >> 2);
+                float x[S + 2 * HL];
+                RDP_UNROLL
+                for (int k = 0; k < S + 2 * HL; ++k) x[k] = gp[k * NG];
+                k3_window_sums<HL, S>(x, a.pf_c, wsum);
+            }
+            uint32_t td[S], tl[S], th[S], acc[S];
+            uint32_t fmask = 0u;                                   // bit j: cell j goes to the exact phase regardless
             RDP_UNROLL
             for (int j = 0; j < S; ++j) {
-                wsum[j] = 0.0f;
+                const float cut = cfar_word_as_float<INT_MODE>(tf[(S * b + HL + j) * SC + s]);
+                float t = cut * a.pf_a;
+                if (a.adaptive) t = fmaxf(t, fminf(cut * a.pf_b, wsum[j]));
+                const uint32_t h = bf16_up(t);
+                tl[j] = h; th[j] = h << 16; td[j] = h | (h << 16);
+                acc[j] = 0u;
+                fmask |= cfar_tiny_cut(cut) ? (1u << j) : 0u;
+            }
+            const int par0 = (s - HC) & 1, pos0 = (s - HC) >> 1;
+            const uint32_t* pa = planes + par0 * PLANE + pos0 * PITCH + (S / 2) * b;            // columns s - HC + even
+            const uint32_t* pb = planes + (par0 ^ 1) * PLANE + (pos0 + par0) * PITCH + (S / 2) * b;   // columns s - HC + odd
+            RDP_UNROLL
+            for (int kk = 0; kk <= 2 * HC; ++kk) {
+                const uint4* src = reinterpret_cast<const uint4*>((kk & 1) ? pb + (kk / 2) * PITCH : pa + (kk / 2) * PITCH);
+                uint32_t w[4 * NPL];
                 RDP_UNROLL
-                for (int k = 0; k <= 2 * HL; ++k) wsum[j] += x[j + k];
-                wsum[j] *= a.pf_c;
+                for (int v = 0; v < NPL; ++v) {
+                    const uint4 u = src[v];
+                    w[4 * v] = u.x; w[4 * v + 1] = u.y; w[4 * v + 2] = u.z; w[4 * v + 3] = u.w;
+                }
+                const bool guard_col = kk - HC >= -GC && kk - HC <= GC;
+                RDP_UNROLL
+                for (int j = 0; j < S; ++j) {
+                    RDP_UNROLL
+                    for (int i = 0; i < NP; ++i) {
+                        // rows 2i, 2i+1 of the support against cell j: window rows j .. j + 2 HL, guard rows j + HL - GL .. j + HL + GL
+                        const int ra = 2 * i, rb = 2 * i + 1;
+                        const bool in_a = ra >= j && ra <= j + 2 * HL && !(guard_col && ra >= j + HL - GL && ra <= j + HL + GL);
+                        const bool in_b = rb >= j && rb <= j + 2 * HL && !(guard_col && rb >= j + HL - GL && rb <= j + HL + GL);
+                        if (in_a && in_b) acc[j] -= bf16x2_lt_mask(w[i], td[j]);
+                        else if (in_a) acc[j] -= bf16x2_lt_mask(w[i], tl[j]);
+                        else if (in_b) acc[j] -= bf16x2_lt_mask(w[i], th[j]);
+                    }
+                }
             }
-        }
-    }
-    RDP_UNROLL
-    for (int p = 0; p < 4; ++p) {
-        const float cut_lo = cfar_as_float(tf[(ty * S + 2 * p + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
-        const float cut_hi = cfar_as_float(tf[(ty * S + 2 * p + 1 + HL) * Sh::SCOLS + tx + Sh::HCP], INT_MODE);
-        float c_lo = cut_lo, c_hi = cut_hi;
-        if (a.adaptive) {
-            c_lo = fmaxf(c_lo * a.pf_a, fminf(c_lo * a.pf_b, wsum[2 * p]));
-            c_hi = fmaxf(c_hi * a.pf_a, fminf(c_hi * a.pf_b, wsum[2 * p + 1]));
-        } else {
-            c_lo *= a.pf_a;
-            c_hi *= a.pf_a;
-        }
-        const uint32_t h0 = bf16_up(c_lo), h1 = bf16_up(c_hi);
-        cb[p] = h0 | (h1 << 16);
-        cl[p] = h0;
-        ch[p] = h1 << 16;
-        acc[p] = 0u;
-        // bfloat16 subnormal range: leave the decision to the exact phase
-        // positive cuts so small that the threshold may fall into the bfloat16 subnormal range (pf_a >= 1e-6) go
-        // to the exact phase; one unsigned compare on the bit pattern covers 0 < cut < 1e-30
-        fmask |= ((uint32_t)__float_as_int(cut_lo) - 1u < 0x0da24260u - 1u) ? (1u << (2 * p)) : 0u;
-        fmask |= ((uint32_t)__float_as_int(cut_hi) - 1u < 0x0da24260u - 1u) ? (2u << (2 * p)) : 0u;
-    }
-    const uint32_t* tp = th + (ty * S) * Sh::SCOLS + tx + Sh::HCP;
-    for (int dc = -HC; dc <= 0; ++dc) {
-        if (dc >= -GC) K3Rows<HL, GL, true, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
-        else K3Rows<HL, GL, false, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
-    }
-    // Half-way exit: a cell needs rank_idx + 1 of its n_ref references below the threshold, so of the HALF_REFS
-    // references in columns -HC .. 0 at least HALF_REFS - (n_ref - rank_idx - 1) must be.  If no cell of the warp's
-    // 32 x S block gets there (noise-only blocks: almost never), the remaining columns cannot change any decision.
-    bool go_on = true;
-    {
-        constexpr int HALF_REFS = (HC - GC) * (2 * HL + 1) + (GC + 1) * (2 * HL - 2 * GL);
-        const int need = HALF_REFS - (a.n_ref - a.rank_idx - 1);
-        if (need > 0) {
-            bool mine = fmask != 0u;
+            uint32_t smask = fmask;
             RDP_UNROLL
-            for (int p = 0; p < 4; ++p) {
-                const uint32_t lo16 = acc[p] & 0xffffu, hi16 = ((acc[p] >> 16) + lo16) & 0xffffu;
-                mine = mine || (int)lo16 >= need || (int)hi16 >= need;
-            }
-            go_on = __any_sync(0xffffffffu, mine);
-        }
-    }
-    if (go_on) {
-        for (int dc = 1; dc <= HC; ++dc) {
-            if (dc <= GC) K3Rows<HL, GL, true, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
-            else K3Rows<HL, GL, false, 0, S + 2 * HL>::run(tp + dc, Sh::SCOLS, cb, cl, ch, acc);
-        }
-    }
-    {
-        // survivors of this strip as a bit mask; most strips have none and skip the list append altogether
-        uint32_t smask = fmask;
-        RDP_UNROLL
-        for (int p = 0; p < 4; ++p) {
-            const uint32_t lo16 = acc[p] & 0xffffu, hi16 = ((acc[p] >> 16) + lo16) & 0xffffu;
-            smask |= ((int)lo16 >= a.rank_idx + 1) ? (1u << (2 * p)) : 0u;
-            smask |= ((int)hi16 >= a.rank_idx + 1) ? (2u << (2 * p)) : 0u;
-        }
-        const int lines_left = a.n_range - (r0 + ty * S);            // strips / columns past the edge of the map
-        if (col >= a.n_doppler || lines_left <= 0) smask = 0u;
-        else if (lines_left < S) smask &= (1u << lines_left) - 1u;
-        if (cfar_out && col < a.n_doppler) {
-            RDP_UNROLL
-            for (int j = 0; j < S; ++j)
-                if (j < lines_left) cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)(r0 + ty * S + j) * a.n_doppler + col] = 0.0f;
-        }
-        if (smask) {
-            int slot = atomicAdd(n_surv, __popc(smask));
-            while (smask) {
-                const int j = __ffs(smask) - 1;
-                smask &= smask - 1u;
-                surv[slot++] = (unsigned short)((ty * S + j) * TCOLS + tx);
+            for (int j = 0; j < S; ++j) smask |= ((int)(k3_lo_count(acc[j]) + k3_hi_count(acc[j])) >= need) ? (1u << j) : 0u;
+            const int lines_left = a.n_range - (r0 + S * b);            // strips / columns past the edge of the map
+            if (c0 + tx >= a.n_doppler || lines_left <= 0) smask = 0u;
+            else if (lines_left < S) smask &= (1u << lines_left) - 1u;
+            if (smask) {
+                int slot = atomicAdd(ctr + 1, __popc(smask));
+                while (smask) {
+                    const int j = __ffs(smask) - 1;
+                    smask &= smask - 1u;
+                    surv[slot++] = (unsigned short)((S * b + j) * TC + tx);
+                }
             }
         }
     }
@@ -526,18 +621,18 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     // ---- phase 2: exact decision from the raw tile: G lanes per survivor, 32/G survivors per warp pass ---
     // Window slots are dealt to the G lanes (slot = sub + G q); guard / padding slots read the zero cell and
     // their known contribution to each count is subtracted.  Counting = sign bit of an exact float subtraction.
-    const int ns = *n_surv;
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    {
+    const int ns = ctr[1];
     constexpr int G = Sh::G, NQ = Sh::NQ, NZ = Sh::NZ;
     const int sub = lane % G, grp = lane / G;
     const bool n_ref_pow2 = (a.n_ref & (a.n_ref - 1)) == 0;
     const double inv_n = 1.0 / (double)a.n_ref;
-    for (int i0 = warp * (32 / G); i0 < ns; i0 += 8 * (32 / G)) {
+    for (int i0 = warp * (32 / G); i0 < ns; i0 += NWARP * (32 / G)) {
         const int i = i0 + grp;
         const bool valid = i < ns;
         const int code = valid ? (int)surv[i] : 0;                 // idle groups chew on tile cell (0, 0)
-        const int tl = code / TCOLS, tcx = code % TCOLS;
-        const int cidx = (tl + HL) * Sh::SCOLS + tcx + Sh::HCP;
+        const int tl = code / TC, tcx = code % TC;
+        const int cidx = (tl + HL) * SC + tcx + HCP;
         bool det;
         if (!INT_MODE) {
         const float cut = tf[cidx];
@@ -621,22 +716,40 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         det = valid && cut > 0 && (c - NZ) >= a.rank_idx + 1;
         }
-        const float cut = tf[cidx];                                // raw word: written back unchanged in either mode
         if (det && sub == 0) {
             atomicOr(bits + tl * Sh::TWORDS + (tcx >> 5), 1u << (tcx & 31));
-            if (cfar_out)
-                cfar_out[map * (long long)a.n_range * a.n_doppler + (long long)(r0 + tl) * a.n_doppler + c0 + tcx] = cut;
+            if (cfar_out) cfar_out[out_base + (long long)(r0 + tl) * a.n_doppler + c0 + tcx] = tf[cidx];   // raw word, unchanged in either mode
         }
     }
+    }
+    } else {
+    // ---- a tile with negative words: every cell decided exactly by one warp (sign-safe, slow) ---------------
+    for (int cell = warp; cell < TR * TC; cell += NWARP) {
+        const int tl = cell / TC, tcx = cell % TC;
+        if (r0 + tl >= a.n_range || c0 + tcx >= a.n_doppler) continue;
+        const float* ctr_cell = tf + (tl + HL) * SC + tcx + HCP;
+        const float cut = *ctr_cell;
+        const bool det = cfar_exact_warp<Sh::MAXQ>(a, [&](int dl, int dc) { return ctr_cell[dl * SC + dc]; }, cut, lane);
+        if (lane == 0) {
+            if (det) atomicOr(bits + tl * Sh::TWORDS + (tcx >> 5), 1u << (tcx & 31));
+            if (cfar_out) cfar_out[out_base + (long long)(r0 + tl) * a.n_doppler + c0 + tcx] = det ? cut : 0.0f;
+        }
+    }
+    }
     __syncthreads();
-    // bitmask of this tile: rows r0.., words (c0 / 32)..  (TCOLS is a multiple of 32 so tiles own whole words)
+#ifndef RDP_EMU
+    if (use_tma && NSTAGE == 1 && threadIdx.x == 0 && tile_id + (int)gridDim.x < n_tiles32) issue(tile_id + gridDim.x, 0);
+#endif
+    if (threadIdx.x == 0) { ctr[0] = 0; ctr[1] = 0; ctr[2 + (iter & 1)] = 0; }
+    // bitmask of this tile: rows r0.., words (c0 / 32)..  (TC is a multiple of 32 so tiles own whole words)
     uint32_t* bm = det_bits + map * (long long)a.n_range * a.words_per_row;
-    for (int i = threadIdx.x; i < Sh::TROWS * Sh::TWORDS; i += 256) {
+    for (int i = threadIdx.x; i < TR * Sh::TWORDS; i += THREADS) {
         const int rl = i / Sh::TWORDS, w = i % Sh::TWORDS;
         const int line = r0 + rl, word = c0 / 32 + w;
         if (line < a.n_range && word < a.words_per_row) bm[(long long)line * a.words_per_row + word] = bits[i];
+        bits[i] = 0u;
     }
-    __syncthreads();                                      // the tile's shared state is reused by the next tile
+    // (the next tile's first shared-memory writes that anyone else reads come after its own barriers)
     }   // tile loop
 }
 
@@ -662,7 +775,7 @@ k3_cfar_generic_kernel(const float* __restrict__ rd_map, float* __restrict__ cfa
             const int col = word * 32 + b;
             if (col >= a.n_doppler) break;
             const float cv = __ldg(m + (long long)line * a.n_doppler + col);
-            const bool det = cfar_exact_warp<MAXQ_GENERIC>(a, m, line, col, cv, lane);
+            const bool det = cfar_exact_warp<MAXQ_GENERIC>(a, [&](int dl, int dc) { return cfar_fetch(m, line + dl, col + dc, a.n_range, a.n_doppler, a.raster); }, cv, lane);
             if (det) out |= 1u << b;
             if (lane == 0 && cfar_out) cfar_out[map * cells_per_map + (long long)line * a.n_doppler + col] = det ? cv : 0.0f;
         }

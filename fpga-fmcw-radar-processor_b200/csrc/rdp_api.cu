@@ -210,50 +210,55 @@ bool k2_for(int n, K2Launcher* out) {
 }
 
 // ---- K3 dispatch ---------------------------------------------------------------------------
-template <int HL, int HC, int GL, int GC, int S, int TCOLS>
+template <int HL, int HC, int GL, int GC, int TR, int NSTAGE>
 struct K3Inst {
-    using Sh = K3Shape<HL, HC, GL, GC, S, TCOLS>;
+    using Sh = K3Shape<HL, HC, GL, GC, TR, NSTAGE>;
     static cudaError_t prepare(size_t s, int* occ) {
-        cudaError_t e = prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS, true>, 256, s, nullptr);
+        cudaError_t e = prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, true>, Sh::THREADS, s, nullptr);
         if (e != cudaSuccess) return e;
-        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS, false>, 256, s, occ);
+        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, false>, Sh::THREADS, s, occ);
     }
     static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out,
                        uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
                        const CUtensorMap* tmap) {
         if (a.int_mode)
-            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS, true>), (unsigned)grid, 256, s, st, rd_map, cfar_out,
+            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, true>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
                        det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
         else
-            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, S, TCOLS, false>), (unsigned)grid, 256, s, st, rd_map, cfar_out,
+            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, false>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
                        det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
     }
     static K3Launcher get() {
-        return K3Launcher{Sh::TROWS, TCOLS, Sh::SROWS, Sh::SCOLS, Sh::smem_bytes(), &prepare, &launch};
+        return K3Launcher{TR, Sh::TC, Sh::SR, Sh::SC, Sh::smem_bytes(), &prepare, &launch};
     }
 };
 struct K3Generic {
-    static cudaError_t prepare(size_t, int* occ) { if (occ) *occ = 1; return cudaSuccess; }
+    static cudaError_t prepare(size_t, int* occ) { if (occ) *occ = 64; return cudaSuccess; }
     static void launch(long long grid, size_t, cudaStream_t st, const float* rd_map, float* cfar_out,
-                       uint32_t* det_bits, CfarArgs a, int, int, long long, int, const CUtensorMap*) {
-        long long n_words = grid;   // grid carries the bitmask word count for the generic kernel
+                       uint32_t* det_bits, CfarArgs a, int, int, long long, int cap, const CUtensorMap*) {
+        long long n_words = grid;   // grid carries the bitmask word count for the generic kernel, `use_tma` its CTA cap
         long long blocks = (n_words + 7) / 8;
-        if (blocks > 148 * 64) blocks = 148 * 64;
+        if (blocks > cap) blocks = cap;
         RDP_LAUNCH(k3_cfar_generic_kernel, (unsigned)blocks, 256, 0, st, rd_map, cfar_out, det_bits, a, n_words);
     }
     static K3Launcher get() { return K3Launcher{0, 0, 0, 0, 0, &prepare, &launch}; }
 };
 
-K3Launcher k3_for(int hl, int hc, int gl, int gc) {
-#define RDP_K3_CASE(HL, HC, GL, GC, S, TC) \
-    if (hl == HL && hc == HC && gl == GL && gc == GC) return K3Inst<HL, HC, GL, GC, S, TC>::get();
-    RDP_K3_CASE(5, 6, 1, 2, 8, 64)      // radar_core.vhd:376-382 defaults (4,4,2,1), as built
-    RDP_K3_CASE(6, 5, 2, 1, 8, 64)      // same, as named
-    RDP_K3_CASE(3, 4, 1, 1, 8, 64)      // tb_os_cfar_2d.vhd:16-19 (3,2,1,1), as built
-    RDP_K3_CASE(4, 3, 1, 1, 8, 64)      // same, as named
-    RDP_K3_CASE(3, 3, 1, 1, 8, 64)      // legacy quick config (2,2,1,1)
-    RDP_K3_CASE(10, 12, 2, 4, 8, 64)    // BASELINE config 4 "wide" (8,8,4,2), as built
-    RDP_K3_CASE(12, 10, 4, 2, 8, 64)    // same, as named
+// `variant` (RDP_K3_VARIANT, A/B measurements of the default window only): 0 = 64-line tiles, one raw stage;
+// 1 = 64 lines, two stages; 2 = 32 lines, one stage; 3 = 32 lines, two stages
+K3Launcher k3_for(int hl, int hc, int gl, int gc, int variant) {
+#define RDP_K3_CASE(HL, HC, GL, GC, TR, NS) \
+    if (hl == HL && hc == HC && gl == GL && gc == GC) return K3Inst<HL, HC, GL, GC, TR, NS>::get();
+    if (variant == 1) { RDP_K3_CASE(5, 6, 1, 2, 64, 2) }
+    if (variant == 2) { RDP_K3_CASE(5, 6, 1, 2, 32, 1) }
+    if (variant == 3) { RDP_K3_CASE(5, 6, 1, 2, 32, 2) }
+    RDP_K3_CASE(5, 6, 1, 2, 64, 1)      // radar_core.vhd:376-382 defaults (4,4,2,1), as built
+    RDP_K3_CASE(6, 5, 2, 1, 64, 1)      // same, as named
+    RDP_K3_CASE(3, 4, 1, 1, 64, 1)      // tb_os_cfar_2d.vhd:16-19 (3,2,1,1), as built
+    RDP_K3_CASE(4, 3, 1, 1, 64, 1)      // same, as named
+    RDP_K3_CASE(3, 3, 1, 1, 64, 1)      // legacy quick config (2,2,1,1)
+    RDP_K3_CASE(10, 12, 2, 4, 64, 1)    // BASELINE config 4 "wide" (8,8,4,2), as built
+    RDP_K3_CASE(12, 10, 4, 2, 64, 1)    // same, as named
 #undef RDP_K3_CASE
     return K3Generic::get();
 }
@@ -309,6 +314,10 @@ struct rdp_handle {
     K2Launcher k2;
     K3Launcher k3;
     int k1_grid_cap = 1, k2_grid_cap = 1, k3_grid_cap = 1;
+    int knob_k3_ctas = 0, knob_k12_ctas = 0;
+    int knob_k1_cluster = -1;       // RDP_K1_CLUSTER: -1 = automatic (sharded mode only), 0 / 1 = forced off / on
+    int stream_spec_dets = kStreamSpecDets;
+    int k3_variant = 0;             // RDP_K3_VARIANT (tile shape / staging depth of the default CFAR window, A/B measurements)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved at create (NULL: manual tile loads)
     int cfar_tma = 0;               // last CFAR launch staged its tiles with TMA
     int k1_tile_chirps = 1;
@@ -405,9 +414,9 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1
     // The cluster variant pays for its 128-byte segments with 8-byte distributed-shared-memory stores: measured 2.4x
     // slower than the plain kernel into local HBM (1024 x 4096: 45 vs 19 ms per 1024 CPIs), 15 % faster when the
     // segments are peer stores over NVLink (profiles/r1_summary.md) -- so it serves the sharded mode only.
-    // RDP_K1_CLUSTER=0 / 1 forces it off / on (A/B measurements).
+    // RDP_K1_CLUSTER=0 / 1 (read at create) forces it off / on (A/B measurements).
     bool use_cluster = h->k1_max_clusters > 0 && sc.world > 1;
-    if (const char* e = std::getenv("RDP_K1_CLUSTER")) use_cluster = h->k1_max_clusters > 0 && std::atoi(e) != 0;
+    if (h->knob_k1_cluster >= 0) use_cluster = h->k1_max_clusters > 0 && h->knob_k1_cluster != 0;
     if (use_cluster) {
         const long long ctiles = total / h->k1.cs;
         const int n_clusters = (int)(ctiles < h->k1_max_clusters ? ctiles : h->k1_max_clusters);
@@ -458,17 +467,20 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     }
     const long long maps = (long long)n_cpi * c.n_channels;
     if (maps == 0) return RDP_OK;
+    if (h->k3.trows != 0) {
+        const long long tiles = maps * ((c.n_samples + h->k3.trows - 1) / h->k3.trows) * ((c.n_chirps + h->k3.tcols - 1) / h->k3.tcols);
+        if (tiles >= (1ll << 31)) return fail(h, RDP_E_CAPACITY, "CFAR stage: too many tiles in one launch; lower chunk_cpis");
+    }
     stage_begin(h, 2);
     CUtensorMap tmap;
     std::memset(&tmap, 0, sizeof(tmap));
     if (h->k3.trows == 0) {
         h->k3.launch(maps * c.n_samples * args.words_per_row, 0, h->cur, rd_map, cfar_out, h->det_bits, args, 0, 0,
-                     0, 0, &tmap);
+                     0, h->k3_grid_cap, &tmap);
     } else {
         const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
         const int tiles_c = (c.n_chirps + h->k3.tcols - 1) / h->k3.tcols;
         const long long n_tiles = maps * tiles_r * tiles_c;
-        if (n_tiles >= (1ll << 31)) return fail(h, RDP_E_CAPACITY, "CFAR stage: too many tiles in one launch; lower chunk_cpis");
         int use_tma = 0;
 #ifndef RDP_EMU
         // TMA stages the (tile + halo) box and zero-fills outside the map == cfar_edges ZERO; the flat-raster
@@ -627,6 +639,15 @@ int init_handle(rdp_handle* h) {
     RDP_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     RDP_CUDA(h, cudaStreamCreateWithFlags(&h->cfar_stream, cudaStreamNonBlocking));
     h->cur = h->stream;
+    {   // every RDP_* tuning knob is read ONCE, here (rdp.h lists them); nothing on a launch path calls getenv
+        const char* e;
+        if ((e = std::getenv("RDP_OVERLAP"))) h->overlap = std::atoi(e);
+        if ((e = std::getenv("RDP_K3_VARIANT"))) h->k3_variant = std::atoi(e);
+        if ((e = std::getenv("RDP_K3_CTAS"))) h->knob_k3_ctas = std::atoi(e);
+        if ((e = std::getenv("RDP_K12_CTAS"))) h->knob_k12_ctas = std::atoi(e);
+        if ((e = std::getenv("RDP_K1_CLUSTER"))) h->knob_k1_cluster = std::atoi(e) != 0;
+        if ((e = std::getenv("RDP_STREAM_SPEC")) && std::atoi(e) > 0) h->stream_spec_dets = std::atoi(e);
+    }
     for (int i = 0; i < 2; ++i) {
         RDP_CUDA(h, cudaEventCreateWithFlags(&h->ev_map_ready[i], cudaEventDefault));
         RDP_CUDA(h, cudaEventCreateWithFlags(&h->ev_cfar_done[i], cudaEventDefault));
@@ -705,18 +726,14 @@ int init_handle(rdp_handle* h) {
     a.is1 = (int)a.s1; a.ismin = c.scale_min; a.isnom = c.scale_nom; a.ismax = c.scale_max;
     a.max_dets = c.max_dets_per_cpi;
     a.words_per_row = (c.n_chirps + 31) / 32;
-    h->k3 = k3_for(a.half_l, a.half_c, a.guard_l, a.guard_c);
+    h->k3 = k3_for(a.half_l, a.half_c, a.guard_l, a.guard_c, h->k3_variant);
     RDP_CUDA(h, h->k3.prepare(h->k3.smem, &occ));
     h->k3_grid_cap = h->sm_count * occ;
-    {   // tuning knobs: RDP_OVERLAP=1 runs CFAR of chunk i concurrently with the FFT kernels of chunk i+1;
-        // RDP_K3_CTAS / RDP_K12_CTAS cap the persistent CTAs per SM so that both can be co-resident
-        const char* e;
-        if ((e = std::getenv("RDP_OVERLAP"))) h->overlap = std::atoi(e);
-        if ((e = std::getenv("RDP_K3_CTAS")) && std::atoi(e) > 0) h->k3_grid_cap = h->sm_count * std::atoi(e);
-        if ((e = std::getenv("RDP_K12_CTAS")) && std::atoi(e) > 0) {
-            h->k1_grid_cap = h->sm_count * std::atoi(e);
-            h->k2_grid_cap = h->sm_count * std::atoi(e);
-        }
+    // RDP_K3_CTAS / RDP_K12_CTAS cap the persistent CTAs per SM (co-residency experiments)
+    if (h->knob_k3_ctas > 0) h->k3_grid_cap = h->sm_count * h->knob_k3_ctas;
+    if (h->knob_k12_ctas > 0) {
+        h->k1_grid_cap = h->sm_count * h->knob_k12_ctas;
+        h->k2_grid_cap = h->sm_count * h->knob_k12_ctas;
     }
 #ifndef RDP_EMU
     {
@@ -1354,8 +1371,7 @@ int rdp_stream_submit(rdp_handle* h, int32_t slot, const void* cube, int32_t n_c
     // suffices for ordinary scenes; rdp_stream_wait fetches the rest of an unusually long list
     {
         size_t spec = (size_t)n_cpi * c.max_dets_per_cpi;
-        int per_cpi = kStreamSpecDets;
-        if (const char* e = std::getenv("RDP_STREAM_SPEC")) per_cpi = std::atoi(e) > 0 ? std::atoi(e) : per_cpi;   // tests
+        const int per_cpi = h->stream_spec_dets;                  // RDP_STREAM_SPEC at create (tests shrink it)
         if (spec > (size_t)n_cpi * per_cpi) spec = (size_t)n_cpi * per_cpi;
         sl.spec = (long long)spec;
         RDP_CUDA(h, cudaMemcpyAsync(sl.h_packed, sl.d_packed, sizeof(rdp_det) * spec, cudaMemcpyDeviceToHost, sl.copy));

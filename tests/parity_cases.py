@@ -139,6 +139,79 @@ def case_end_to_end(make_core, n_cpi, n_ch, n_chirps, n_samples, seed=11, fmt="i
     return len(dets), len(diff)
 
 
+def case_cfar_signed_map(make_core, n_range=64, n_doppler=64, seed=5, **kw):
+    """Maps with NEGATIVE words (a dB map below 0 dB, a signed caller map): the packed pre-filters assume
+    magnitudes >= 0, so such tiles take the exact sign-safe path -- the dense output and the list must still be
+    bit-exact against the oracle, including tiles that only see a negative word in their halo."""
+    rng = np.random.default_rng(seed)
+    m = np.empty((2, n_range, n_doppler), np.float32)
+    m[0] = (20.0 * np.log10(rng.rayleigh(1e-4, size=(n_range, n_doppler)))).astype(np.float32)   # all below 0 dB
+    m[0, n_range // 3, n_doppler // 3] = -20.0
+    m[1] = rng.rayleigh(60.0, size=(n_range, n_doppler)).astype(np.float32)          # ordinary map ...
+    m[1, 5, 7] = 900.0
+    m[1, n_range - 9, n_doppler - 4] = 1500.0
+    m[1, n_range // 2, n_doppler // 2] = -3.0                                          # ... with one negative word,
+    m[1, 2, 3] = -0.0                                                                  # a negative zero
+    m[1, 10:14, 20] = 0.0                                                              # and exact zeros
+    kw.setdefault("max_dets_per_cpi", 2 * n_range * n_doppler)                          # nearly every cell of the dB map is a "detection"
+    with make_core(n_range=n_range, n_doppler=n_doppler, n_channels=2, **kw) as c:
+        dets, counts, status, dense = c.cfar_stage(m[None])
+    okw = {k: v for k, v in kw.items() if k in fp.DEFAULTS}
+    exp = np.stack([fp.cfar_stage(m[i], **okw) for i in range(2)])
+    assert np.array_equal(dense[0], exp)
+    ref = np.concatenate([fp.detections(exp[i], 0, i) for i in range(2)])
+    assert counts.tolist() == [len(ref)] and len(ref) > 0
+    for f in ("channel", "range", "doppler", "mag"):
+        assert np.array_equal(dets[f], ref[f]), f
+    assert int((ref["mag"] < 0).sum()) > 0                                             # negative detections exist and match
+
+
+def case_end_to_end_mag_modes(make_core, n_ch=2, n_chirps=32, n_samples=64, seed=23):
+    """Whole path with mag_mode pow and logpow (north_star: |X|^2 and the log magnitude), CFAR included, against the
+    oracle -- once on an int16 cube (dB values far above 0) and once on a complex64 cube so weak that |X|^2 < 1
+    (every dB value negative: the sign-safe CFAR path).  CFAR on a dB map keeps the reference's MULTIPLICATIVE rule
+    (os_cfar_2d.vhd:204,213 knows no other); it is a defined function of the map, not a sensible detector."""
+    out = {}
+    for fmt, scale in (("int16", 1.0), ("complex64", 1e-9)):
+        cube, _ = st.synthetic_cube(2, n_ch, n_chirps, n_samples, seed=seed, dtype=fmt, sigma=30.0, n_targets=(2, 3))
+        if fmt == "complex64":
+            cube = (cube * np.float32(scale)).astype(np.complex64)
+        for mode in ("pow", "logpow"):
+            with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, input_format=fmt, max_cpis=2,
+                           mag_mode=mode, max_dets_per_cpi=1 << 16) as c:
+                rd_map, dets, n_dets, status = (x.copy() for x in c.process(cube))
+            ref_map, ref_dets, ref_counts = fp.process_batch(cube, mag_mode=mode)
+            if mode == "logpow":
+                # compare in the linear domain (the dB value of a near-null cell is ill-conditioned) ...
+                assert rel_err(10.0 ** (rd_map.astype(np.float64) / 10.0), 10.0 ** (ref_map.astype(np.float64) / 10.0)) <= 1e-5
+                err = float(np.abs(rd_map - ref_map).max())                            # ... and bound the dB error itself
+                assert err <= 0.5, err
+                strong = ref_map >= ref_map.max() - 60.0
+                assert float(np.abs(rd_map - ref_map)[strong].max()) <= 1e-2
+                if scale != 1.0:
+                    assert float(ref_map.max()) < 0.0                                  # the all-negative case really is one
+            else:
+                err = float(np.abs(rd_map - ref_map).max())
+                assert err <= 4 * MAP_TOL * float(ref_map.max())
+            # the CFAR stage on the GPU's own map is bit-exact against the oracle's CFAR on that same map
+            exp = np.concatenate([fp.detections(fp.cfar_stage(rd_map[i, ch]), i, ch) for i in range(2) for ch in range(n_ch)])
+            assert len(exp) == len(dets) and status.tolist() == [0, 0], (fmt, mode)
+            # (a dB map far above 0 dB has no cell 2..6 TIMES its neighbours: the multiplicative rule finds nothing there)
+            assert len(dets) > 0 or (mode == "logpow" and scale == 1.0), (fmt, mode)
+            for f in ("cpi", "channel", "range", "doppler", "mag"):
+                assert np.array_equal(dets[f], exp[f]), (fmt, mode, f)
+            # and the list from the oracle's map differs only in near-threshold cells
+            eps = max(4.0 * err, 1e-7 * float(np.abs(ref_map).max()))
+            diff = det_cells(dets) ^ det_cells(ref_dets)
+            amb = {}
+            for (i, ch, r, d) in diff:
+                if (i, ch) not in amb:
+                    amb[(i, ch)] = fp.ambiguous_cells(ref_map[i, ch], eps, mag_mode=mode)
+                assert amb[(i, ch)][r, d], (fmt, mode, i, ch, r, d)
+            out[(fmt, mode)] = (len(dets), len(diff))
+    return out
+
+
 def case_overflow_flag(make_core):
     m = rayleigh_map(64, 64, seed=5, n_maps=1)
     m[0, 10:30, 10:30:3] = 9000.0                          # many isolated strong cells

@@ -61,6 +61,16 @@ def test_cfar_tb_map(make_core):
     pc.case_cfar_tb_map(make_core)
 
 
+@pytest.mark.parametrize("nr,nd,kw", [(32, 64, dict()), (64, 128, dict(cfar_edges="raster", cfar_axes="as_named")),
+                                      (32, 64, dict(scale_override=2))])
+def test_cfar_signed_map(make_core, nr, nd, kw):
+    pc.case_cfar_signed_map(make_core, nr, nd, **kw)
+
+
+def test_end_to_end_mag_modes(make_core):
+    pc.case_end_to_end_mag_modes(make_core)
+
+
 def test_end_to_end(make_core):
     pc.case_end_to_end(make_core, 2, 2, 32, 64)
 
