@@ -5,4 +5,5 @@ from .rdp import (DET_DTYPE, TRACK_DTYPE, DeviceBuffer, RadarCore, RdpError, loa
                   process_cpi)
 from .io_text import read_detections, write_detections, write_tracks  # noqa: F401
 from .sharding import merge_detections, shard_cpis  # noqa: F401
-from .sharded import ShardedCpi, TorchExchange  # noqa: E402,F401
+from .sharded import ShardedCpi  # noqa: E402,F401
+from .exchange import SocketExchange  # noqa: E402,F401

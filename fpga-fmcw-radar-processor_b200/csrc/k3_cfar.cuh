@@ -63,6 +63,9 @@ struct CfarArgs {
     // pre-filter threshold: T = max(cut * pf_a, min(cut * pf_b, window_sum * pf_c))
     // (non-adaptive: pf_a = 1.001 / s1, pf_b = pf_c = 0)
     float pf_a, pf_b, pf_c;
+    int skew_div;                           // CTAs per residency slot (= SM count)
+    int skew_ns;                            // RDP_K3_SKEW_NS: start-up skew between the CTAs that share an SM (see the kernel)
+    int debug_skip;                         // RDP_K3_DEBUG_SKIP (timing experiments only; results are WRONG when set): 1 = no phases 1 / 2, 2 = no phase 0, 4 = no conversion
 };
 
 // magnitude word -> float for the pre-filter; integers below 2^24 convert exactly
@@ -197,15 +200,17 @@ struct K3Shape {
     static constexpr int G = WIN <= 160 ? 8 : (WIN <= 320 ? 16 : 32);
     // (the slot table lists the reference cells only, padded to a multiple of G with slots that read a zero cell)
     static constexpr int NQ = (NREF + G - 1) / G, NSLOT = NQ * G, NZ = NSLOT - NREF;
-    static constexpr int ZERO_IDX = SRP * SC;
-    static constexpr int TF_WORDS = (SRP * SC + 4 + 31) / 32 * 32;    // one raw stage (+ a cell that reads 0.0f), 128 B multiple
+    static constexpr int ZERO_IDX = SR * SC;
+    static constexpr int TF_WORDS = (SR * SC + 4 + 31) / 32 * 32;     // one raw stage (+ a cell that reads 0.0f), 128 B multiple
+    // phase 1 runs in rounds of STRIPS_PER_ROUND strips so that their survivors (<= 8 each) always fit the list
+    static constexpr int STRIPS_PER_ROUND = 128, SURV_CAP = S * STRIPS_PER_ROUND;
     static constexpr int TILE_BYTES = SR * SC * 4;
     static constexpr int N_STRIPS = NBAND * TC;
     static_assert(TR % S == 0 && TR * TC <= 65536 && (SC % 4) == 0 && (PITCH % 8) == 4 && PITCH % 4 == 0, "tile geometry");
     static_assert(4 * NCOV >= 2 * HC + 1 + 3 && 4 * NCOV >= 2 * HC + 2 + (HC % 2 ? 3 : 2), "NCOV groups cover the window at any alignment");
     static constexpr size_t smem_bytes() {
-        return sizeof(float) * ((size_t)NSTAGE * TF_WORDS + SRP * NG) + sizeof(uint32_t) * (2 * PLANE + TR * TWORDS) +
-               sizeof(unsigned short) * (N_STRIPS + TR * TC) + sizeof(int) * (8 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
+        return sizeof(float) * ((size_t)NSTAGE * TF_WORDS + SR * NG) + sizeof(uint32_t) * (2 * PLANE + TR * TWORDS) +
+               sizeof(unsigned short) * (N_STRIPS + SURV_CAP) + sizeof(int) * (8 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
     }
     static constexpr int occupancy_hint() {                        // CTAs per SM the shared memory allows (<= 2048 threads)
         int n = (int)((227 * 1024) / (smem_bytes() + 1024));
@@ -243,6 +248,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+// the same box pulled into L2 only (no shared-memory destination): issued a tile ahead of the load that needs it
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(x), "r"(y), "r"(z) : "memory");
 }
 #endif
 
@@ -311,8 +320,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     unsigned char* smem_al = smem_raw + ((128 - ((uintptr_t)smem_raw & 127)) & 127);
     float* tf0 = reinterpret_cast<float*>(smem_al);                             // raw magnitudes
     uint32_t* planes = reinterpret_cast<uint32_t*>(tf0 + NSTAGE * Sh::TF_WORDS);  // [2][SC / 2][PITCH] bf16 row pairs
-    float* cov = reinterpret_cast<float*>(planes + 2 * PLANE);                  // [SRP][NG] sums of the 4 NCOV columns from group g on
-    uint32_t* bits = reinterpret_cast<uint32_t*>(cov + SRP * NG);               // [TR][TWORDS]
+    float* cov = reinterpret_cast<float*>(planes + 2 * PLANE);                  // [SR][NG] sums of the 4 NCOV columns from group g on
+    uint32_t* bits = reinterpret_cast<uint32_t*>(cov + SR * NG);                // [TR][TWORDS]
     int* ctr = reinterpret_cast<int*>(bits + TR * Sh::TWORDS);                  // 0: strips listed, 1: survivors listed, 2 / 3: tile holds a negative word (by iteration parity)
     int* wtab = ctr + 8;                                                        // [NSLOT][2]: tf index = ctr * mul + add
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wtab + 2 * Sh::NSLOT);
@@ -322,12 +331,12 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int need = a.rank_idx + 1;
 
-    // rows SR .. SRP-1 of every raw stage and its zero cell are never written again
+    // the zero cell behind every raw stage is never written again
     for (int st = 0; st < NSTAGE; ++st)
         for (int i = SR * SC + threadIdx.x; i < Sh::TF_WORDS; i += THREADS) tf0[st * Sh::TF_WORDS + i] = 0.0f;
     for (int i = threadIdx.x; i < TR * Sh::TWORDS; i += THREADS) bits[i] = 0u;
     if (threadIdx.x == 0) {
-        ctr[0] = 0; ctr[1] = 0; ctr[2] = 0; ctr[3] = 0;
+        for (int i = 0; i < 8; ++i) ctr[i] = 0;
 #ifndef RDP_EMU
         if (use_tma) {
             mbar_init(mbar, 1);
@@ -364,9 +373,22 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         mbar_expect_tx(mbar + st, (uint32_t)Sh::TILE_BYTES);
         tma_load_3d(tf0 + st * Sh::TF_WORDS, tmap_ptr, mbar + st, (rem % tiles_c) * TC - HCP, (rem / tiles_c) * TR - HL, (int)mp);
     };
+    auto prefetch = [=](int t) {
+        const int mp = t / tiles_per_map;
+        const int rem = t - mp * tiles_per_map;
+        tma_prefetch_3d(tmap_ptr, (rem % tiles_c) * TC - HCP, (rem / tiles_c) * TR - HL, (int)mp);
+    };
     if (use_tma && threadIdx.x == 0 && (long long)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
 #endif
 
+#ifndef RDP_EMU
+    // CTAs that share an SM start in lock-step and would run their issue-bound phase together and then their
+    // latency-bound phases together; a one-off skew by residency slot lets one CTA's phase 0 fill another's gaps
+    if (a.skew_ns > 0) {
+        const unsigned slot = blockIdx.x / (unsigned)a.skew_div;
+        for (unsigned i = 0; i < slot; ++i) __nanosleep((unsigned)a.skew_ns);
+    }
+#endif
     int iter = 0;
     const int n_tiles32 = (int)n_tiles;
     for (int tile_id = blockIdx.x; tile_id < n_tiles32; tile_id += gridDim.x, ++iter) {
@@ -385,6 +407,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         // ended the previous iteration) while this one is processed; one stage: it was issued at the end of the
         // previous iteration and other CTAs of the SM cover the latency
         if (NSTAGE == 2 && threadIdx.x == 0 && tile_id + (int)gridDim.x < n_tiles32) issue(tile_id + gridDim.x, stage ^ 1);
+        // one stage: the next tile cannot land in shared memory yet, but it can be on its way into L2
+        if (NSTAGE == 1 && (a.debug_skip & 8) == 0 && threadIdx.x == 32 && tile_id + (int)gridDim.x < n_tiles32) prefetch(tile_id + gridDim.x);
         mbar_wait(mbar + stage, (uint32_t)((NSTAGE == 2 ? (iter >> 1) : iter) & 1));
     } else
 #endif
@@ -413,7 +437,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     }
 
     // ---- conversion: raw words -> packed bf16 row pairs (two planes), column-group cover sums, sign check --------
-    {
+    if (!(a.debug_skip & 4)) {
         constexpr int OV = Sh::NCOV - 1, ADV = 32 - OV;
         static_assert(ADV >= 8, "cover shuffles");
         const float4* tf4 = reinterpret_cast<const float4*>(tf);
@@ -426,8 +450,11 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             uint32_t wd[4][4];                                      // [column of the group][row pair]
             RDP_UNROLL
             for (int i = 0; i < 4; ++i) {
-                const float4 ra = tf4[((8 * q + 2 * i) * SC + 4 * g) >> 2];
-                const float4 rb = tf4[((8 * q + 2 * i + 1) * SC + 4 * g) >> 2];
+                // (SR is even: a row pair is inside the staged tile or past its end, where the planes read as zero)
+                const bool in_tile = SR % 8 == 0 || 8 * q + 2 * i < SR;
+                const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const float4 ra = in_tile ? tf4[((8 * q + 2 * i) * SC + 4 * g) >> 2] : zero4;
+                const float4 rb = in_tile ? tf4[((8 * q + 2 * i + 1) * SC + 4 * g) >> 2] : zero4;
                 if (!INT_MODE) {
                     neg |= (uint32_t)__float_as_int(ra.x) | (uint32_t)__float_as_int(ra.y) | (uint32_t)__float_as_int(ra.z) | (uint32_t)__float_as_int(ra.w);
                     neg |= (uint32_t)__float_as_int(rb.x) | (uint32_t)__float_as_int(rb.y) | (uint32_t)__float_as_int(rb.z) | (uint32_t)__float_as_int(rb.w);
@@ -463,20 +490,26 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                         const float nb = __shfl_down_sync(0xffffffffu, gs[k], d);
                         cover += g + d < NG ? nb : 0.0f;
                     }
-                    if (mine) cov[(8 * q + k) * NG + g] = cover;
+                    if (mine && (SR % 8 == 0 || 8 * q + k < SR)) cov[(8 * q + k) * NG + g] = cover;
                 }
             }
         }
         if (!INT_MODE) {
-            if (__any_sync(0xffffffffu, (int)(neg >> 31)) && lane == 0) ctr[2 + (iter & 1)] = 1;
+            if (__any_sync(0xffffffffu, (int)(neg >> 31)) && lane == 0) ctr[4 + (iter & 1)] = 1;
         }
     }
     __syncthreads();
-    const bool signed_tile = !INT_MODE && ctr[2 + (iter & 1)] != 0;   // (reset after the tile; the next tile raises the other flag)
+    // counters alternate by tile parity: this tile's are reset by thread 0 while the NEXT tile is in flight (after
+    // that tile's first barrier, when nobody reads them any more and nobody has written the ones after it yet)
+    const int par = iter & 1;
+    int* const n_strips_ctr = ctr + par;                           // strips listed by phase 0
+    int* const n_surv_ctr = ctr + 2 + par;                         // survivors listed by phase 1, running over the rounds
+    if (threadIdx.x == 0) { ctr[par ^ 1] = 0; ctr[2 + (par ^ 1)] = 0; ctr[4 + (par ^ 1)] = 0; }
+    const bool signed_tile = !INT_MODE && ctr[4 + par] != 0;
 
     if (!signed_tile) {
     // ---- phase 0: one shared threshold per strip ------------------------------------------------------------
-    {
+    if (!(a.debug_skip & 2)) {
         const int b = warp;                                        // band: tile lines 8 b .. 8 b + 7, staged rows 8 b .. 8 b + 7 + 2 HL
         const int s0 = 2 * lane + HCP;                             // staged column of the first of this lane's two columns
         float cm0 = 0.0f, cm1 = 0.0f;                              // largest cut of either strip
@@ -530,7 +563,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         const int n0 = __popc(b0), n1 = __popc(b1);
         if (n0 + n1) {
             int base = 0;
-            if (lane == 0) base = atomicAdd(ctr, n0 + n1);
+            if (lane == 0) base = atomicAdd(n_strips_ctr, n0 + n1);
             base = __shfl_sync(0xffffffffu, base, 0);
             const uint32_t below = (1u << lane) - 1u;
             if (f0) strips[base + __popc(b0 & below)] = (unsigned short)(b * TC + 2 * lane);
@@ -545,10 +578,64 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     }
     __syncthreads();
 
+    // ---- phases 1 and 2 in rounds of STRIPS_PER_ROUND strips (one round unless the tile is crowded) ---------------
+    const int n_strips = (a.debug_skip & 1) ? 0 : *n_strips_ctr;
+    int surv_begin = 0;
+    for (int sbase = 0; sbase < n_strips; sbase += Sh::STRIPS_PER_ROUND) {
     // ---- phase 1: surviving strips, per-cell thresholds -----------------------------------------------------
-    {
-        const int n_strips = ctr[0];
-        for (int idx = threadIdx.x; idx < n_strips; idx += THREADS) {
+    if (n_strips <= THREADS / S) {
+        // few strips (the usual case away from targets): S lanes per strip, one cell each, so that the whole test is
+        // ~300 instructions deep instead of ~1100.  The window membership of a row pair depends on the lane's cell:
+        // it is folded into per-pair threshold operands (0 in a half that is outside the window / inside the guard box:
+        // no magnitude is below 0), and all NP pairs of every column are compared.
+        const int sidx = (int)threadIdx.x / S, j = (int)threadIdx.x % S;
+        if (sidx < n_strips) {
+            const int code = strips[sidx];
+            const int b = code / TC, tx = code % TC;
+            const int s = tx + HCP;
+            const float cut = cfar_word_as_float<INT_MODE>(tf[(S * b + HL + j) * SC + s]);
+            float t = cut * a.pf_a;
+            if (a.adaptive) {
+                const float* gp = cov + (S * b + j) * NG + ((s - HC) >> 2);
+                float w = 0.0f;
+                RDP_UNROLL
+                for (int k = 0; k <= 2 * HL; ++k) w += gp[k * NG];
+                t = fmaxf(t, fminf(cut * a.pf_b, w * a.pf_c));
+            }
+            const uint32_t h = bf16_up(t);
+            uint32_t opn[NP], opg[NP];
+            RDP_UNROLL
+            for (int i = 0; i < NP; ++i) {
+                const int ra = 2 * i, rb = 2 * i + 1;
+                const bool in_a = ra >= j && ra <= j + 2 * HL, in_b = rb >= j && rb <= j + 2 * HL;
+                const bool g_a = ra >= j + HL - GL && ra <= j + HL + GL, g_b = rb >= j + HL - GL && rb <= j + HL + GL;
+                opn[i] = (in_a ? h : 0u) | (in_b ? h << 16 : 0u);
+                opg[i] = (in_a && !g_a ? h : 0u) | (in_b && !g_b ? h << 16 : 0u);
+            }
+            const int par0 = (s - HC) & 1, pos0 = (s - HC) >> 1;
+            const uint32_t* pa = planes + par0 * PLANE + pos0 * PITCH + (S / 2) * b;
+            const uint32_t* pb = planes + (par0 ^ 1) * PLANE + (pos0 + par0) * PITCH + (S / 2) * b;
+            uint32_t acc = 0u;
+            RDP_UNROLL
+            for (int kk = 0; kk <= 2 * HC; ++kk) {
+                const uint4* src = reinterpret_cast<const uint4*>((kk & 1) ? pb + (kk / 2) * PITCH : pa + (kk / 2) * PITCH);
+                uint32_t w[4 * NPL];
+                RDP_UNROLL
+                for (int v = 0; v < NPL; ++v) {
+                    const uint4 u = src[v];
+                    w[4 * v] = u.x; w[4 * v + 1] = u.y; w[4 * v + 2] = u.z; w[4 * v + 3] = u.w;
+                }
+                const bool guard_col = kk - HC >= -GC && kk - HC <= GC;
+                RDP_UNROLL
+                for (int i = 0; i < NP; ++i) acc -= bf16x2_lt_mask(w[i], guard_col ? opg[i] : opn[i]);
+            }
+            const bool keep = ((int)(k3_lo_count(acc) + k3_hi_count(acc)) >= need || cfar_tiny_cut(cut)) &&
+                              c0 + tx < a.n_doppler && r0 + S * b + j < a.n_range;
+            if (keep) surv[atomicAdd(n_surv_ctr, 1) - surv_begin] = (unsigned short)((S * b + j) * TC + tx);
+        }
+    } else {
+        const int idx = sbase + (int)threadIdx.x;
+        if (threadIdx.x < Sh::STRIPS_PER_ROUND && idx < n_strips) {
             const int code = strips[idx];
             const int b = code / TC, tx = code % TC;
             const int s = tx + HCP;                                 // staged column of the strip
@@ -607,7 +694,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             if (c0 + tx >= a.n_doppler || lines_left <= 0) smask = 0u;
             else if (lines_left < S) smask &= (1u << lines_left) - 1u;
             if (smask) {
-                int slot = atomicAdd(ctr + 1, __popc(smask));
+                int slot = atomicAdd(n_surv_ctr, __popc(smask)) - surv_begin;
                 while (smask) {
                     const int j = __ffs(smask) - 1;
                     smask &= smask - 1u;
@@ -622,7 +709,9 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     // Window slots are dealt to the G lanes (slot = sub + G q); guard / padding slots read the zero cell and
     // their known contribution to each count is subtracted.  Counting = sign bit of an exact float subtraction.
     {
-    const int ns = ctr[1];
+    const int surv_end = *n_surv_ctr;
+    const int ns = surv_end - surv_begin;
+    surv_begin = surv_end;
     constexpr int G = Sh::G, NQ = Sh::NQ, NZ = Sh::NZ;
     const int sub = lane % G, grp = lane / G;
     const bool n_ref_pow2 = (a.n_ref & (a.n_ref - 1)) == 0;
@@ -722,6 +811,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         }
     }
     }
+    __syncthreads();                                               // the survivor list is free again; bits of this round are in
+    }   // rounds
     } else {
     // ---- a tile with negative words: every cell decided exactly by one warp (sign-safe, slow) ---------------
     for (int cell = warp; cell < TR * TC; cell += NWARP) {
@@ -735,12 +826,12 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             if (cfar_out) cfar_out[out_base + (long long)(r0 + tl) * a.n_doppler + c0 + tcx] = det ? cut : 0.0f;
         }
     }
-    }
     __syncthreads();
+    }
+    // every read of this tile's raw stage, planes and lists lies before a barrier every thread has passed
 #ifndef RDP_EMU
     if (use_tma && NSTAGE == 1 && threadIdx.x == 0 && tile_id + (int)gridDim.x < n_tiles32) issue(tile_id + gridDim.x, 0);
 #endif
-    if (threadIdx.x == 0) { ctr[0] = 0; ctr[1] = 0; ctr[2 + (iter & 1)] = 0; }
     // bitmask of this tile: rows r0.., words (c0 / 32)..  (TC is a multiple of 32 so tiles own whole words)
     uint32_t* bm = det_bits + map * (long long)a.n_range * a.words_per_row;
     for (int i = threadIdx.x; i < TR * Sh::TWORDS; i += THREADS) {
@@ -749,7 +840,6 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         if (line < a.n_range && word < a.words_per_row) bm[(long long)line * a.words_per_row + word] = bits[i];
         bits[i] = 0u;
     }
-    // (the next tile's first shared-memory writes that anyone else reads come after its own barriers)
     }   // tile loop
 }
 

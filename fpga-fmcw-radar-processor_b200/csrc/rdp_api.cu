@@ -314,7 +314,8 @@ struct rdp_handle {
     K2Launcher k2;
     K3Launcher k3;
     int k1_grid_cap = 1, k2_grid_cap = 1, k3_grid_cap = 1;
-    int knob_k3_ctas = 0, knob_k12_ctas = 0;
+    int knob_k3_ctas = 0, knob_k12_ctas = 0, knob_k3_tiles_per_cta = 0, knob_priority = 1;
+    int knob_k3_debug_skip = 0, knob_k3_skew_ns = 0;
     int knob_k1_cluster = -1;       // RDP_K1_CLUSTER: -1 = automatic (sharded mode only), 0 / 1 = forced off / on
     int stream_spec_dets = kStreamSpecDets;
     int k3_variant = 0;             // RDP_K3_VARIANT (tile shape / staging depth of the default CFAR window, A/B measurements)
@@ -501,7 +502,13 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
         }
 #endif
         h->cfar_tma = use_tma;
-        const long long grid = n_tiles < h->k3_grid_cap ? n_tiles : h->k3_grid_cap;
+        long long grid = n_tiles < h->k3_grid_cap ? n_tiles : h->k3_grid_cap;
+        // RDP_K3_TILES_PER_CTA > 0: more, shorter-lived CTAs than fit at once, so that SM resources turn over and the
+        // FFT kernels of the next chunk (higher-priority stream) get placed between them
+        if (h->knob_k3_tiles_per_cta > 0) {
+            const long long want = (n_tiles + h->knob_k3_tiles_per_cta - 1) / h->knob_k3_tiles_per_cta;
+            if (want > grid) grid = want;
+        }
         h->k3.launch(grid, h->k3.smem, h->cur, rd_map, cfar_out, h->det_bits, args, tiles_r, tiles_c, n_tiles, use_tma,
                      &tmap);
     }
@@ -634,20 +641,29 @@ int init_handle(rdp_handle* h) {
     cudaDeviceProp prop;
     RDP_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
     h->sm_count = prop.multiProcessorCount;
-    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
-    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->cfar_stream, cudaStreamNonBlocking));
-    h->cur = h->stream;
     {   // every RDP_* tuning knob is read ONCE, here (rdp.h lists them); nothing on a launch path calls getenv
         const char* e;
         if ((e = std::getenv("RDP_OVERLAP"))) h->overlap = std::atoi(e);
         if ((e = std::getenv("RDP_K3_VARIANT"))) h->k3_variant = std::atoi(e);
         if ((e = std::getenv("RDP_K3_CTAS"))) h->knob_k3_ctas = std::atoi(e);
+        if ((e = std::getenv("RDP_K3_TILES_PER_CTA"))) h->knob_k3_tiles_per_cta = std::atoi(e);
         if ((e = std::getenv("RDP_K12_CTAS"))) h->knob_k12_ctas = std::atoi(e);
         if ((e = std::getenv("RDP_K1_CLUSTER"))) h->knob_k1_cluster = std::atoi(e) != 0;
+        if ((e = std::getenv("RDP_STREAM_PRIORITY"))) h->knob_priority = std::atoi(e);
+        if ((e = std::getenv("RDP_K3_DEBUG_SKIP"))) h->knob_k3_debug_skip = std::atoi(e);
+        if ((e = std::getenv("RDP_K3_SKEW_NS"))) h->knob_k3_skew_ns = std::atoi(e);
         if ((e = std::getenv("RDP_STREAM_SPEC")) && std::atoi(e) > 0) h->stream_spec_dets = std::atoi(e);
     }
+    // the FFT kernels (HBM-bound) run on `stream`, the CFAR kernels (ALU-bound) of the previous chunk on `cfar_stream`;
+    // the FFT stream has the higher priority so that its CTAs are placed first whenever CFAR CTAs retire
+    int prio_least = 0, prio_greatest = 0;
+    RDP_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    const int prio_fft = h->knob_priority ? prio_greatest : prio_least;
+    RDP_CUDA(h, cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_fft));
+    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    RDP_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    RDP_CUDA(h, cudaStreamCreateWithPriority(&h->cfar_stream, cudaStreamNonBlocking, prio_least));
+    h->cur = h->stream;
     for (int i = 0; i < 2; ++i) {
         RDP_CUDA(h, cudaEventCreateWithFlags(&h->ev_map_ready[i], cudaEventDefault));
         RDP_CUDA(h, cudaEventCreateWithFlags(&h->ev_cfar_done[i], cudaEventDefault));
@@ -723,6 +739,9 @@ int init_handle(rdp_handle* h) {
     if (a.pf_a < 1e-6f) a.pf_a = 1e-6f;                            // keeps thresholds of cuts >= 1e-30 out of the bf16 subnormals
     a.raster = c.cfar_edges == RDP_EDGES_RASTER;
     a.int_mode = 0;
+    a.debug_skip = h->knob_k3_debug_skip;
+    a.skew_ns = h->knob_k3_skew_ns;
+    a.skew_div = h->sm_count > 0 ? h->sm_count : 1;
     a.is1 = (int)a.s1; a.ismin = c.scale_min; a.isnom = c.scale_nom; a.ismax = c.scale_max;
     a.max_dets = c.max_dets_per_cpi;
     a.words_per_row = (c.n_chirps + 31) / 32;

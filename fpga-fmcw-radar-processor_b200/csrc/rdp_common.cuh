@@ -2,7 +2,7 @@
 #pragma once
 
 #ifdef RDP_EMU
-#include "emu/cuda_emu.h"
+#include "cuda_emu.h"          // tests/emu/ (the CPU test harness only; -I tests/emu on that build)
 #else
 #include <cuda_runtime.h>
 #endif

@@ -7,8 +7,8 @@ no separate collective and no repack (`rdp_range_stage_scatter`).  After a barri
 Doppler stage on its n_samples / world range lines, copies the CFAR halo lines from its two neighbours'
 maps, and runs the CFAR stage on (own + halo) lines.  Detections come back with global range indices.
 
-Ranks only need a way to exchange 64-byte IPC handles and to barrier: `TorchExchange` does that with
-torch.distributed (NCCL / gloo); the data itself never goes through a collective.  For the hot path of
+Ranks only need a way to exchange 64-byte IPC handles and to barrier: `exchange.SocketExchange` does that over
+plain TCP sockets (no torch, no MPI); the data itself never goes through a collective.  For the hot path of
 the benchmark none of this is needed -- CPIs shard across GPUs with no exchange at all (sharding.py); this
 mode exists for a CPI too large for one GPU's memory, and is exercised at small sizes by the tests.
 """
@@ -20,23 +20,6 @@ import os
 import numpy as np
 
 from .rdp import DET_DTYPE, RadarCore, RdpError, RdpScatter
-
-
-class TorchExchange:
-    """all_gather of small Python objects + barrier over torch.distributed (already initialised)."""
-
-    def __init__(self):
-        import torch.distributed as dist
-        self.dist = dist
-        self.world, self.rank = dist.get_world_size(), dist.get_rank()
-
-    def all_gather(self, obj):
-        out = [None] * self.world
-        self.dist.all_gather_object(out, obj)
-        return out
-
-    def barrier(self):
-        self.dist.barrier()
 
 
 class ShardedCpi:

@@ -6,7 +6,7 @@
                        not in /root/reference; it is restated from the standard.
 * tb_radar_core_frames / old_tb_radar_core_cube -- the integration-TB stimuli.
 * cfar_tb_map       -- rtl/src/tb_os_cfar_2d.vhd:52-75.
-* synthetic_cube    -- BASELINE.json config 2 / 3 style multi-target cubes.
+* synthetic_cube    -- re-exported from the product's scenario module (BASELINE config 2 / 3 style cubes).
 """
 from __future__ import annotations
 
@@ -121,35 +121,6 @@ def cfar_tb_map(noise_floor=100, tgt_amp=5000, t1=(30, 16), t2=(50, 8), n_range=
     return m.astype(np.uint32)
 
 
-def synthetic_cube(n_cpi, n_channels, n_chirps, n_samples, seed=1234, dtype="int16",
-                   n_targets=(3, 8), amp=(1000.0, 12000.0), sigma=50.0, fixed_targets=None):
-    """SURVEY 8(d) config-3 style cubes: per CPI 3-8 targets with uniformly random
-    (R, D, A), a per-channel phase offset and Gaussian noise sigma per component
-    (as tb_tactical.vhd:59,301-303), default_rng(seed + cpi).
-    Returns (cube [cpi, ch, chirp, sample, 2] int16 or [cpi, ch, chirp, sample]
-    complex64, list of per-CPI target arrays [(R, D, A)])."""
-    s = np.arange(n_samples, dtype=np.float64)[None, :]
-    c = np.arange(n_chirps, dtype=np.float64)[:, None]
-    out = []
-    truth = []
-    for i in range(n_cpi):
-        rng = np.random.default_rng(seed + i)
-        if fixed_targets is not None:
-            tg = np.asarray(fixed_targets, dtype=np.float64)
-        else:
-            nt = int(rng.integers(n_targets[0], n_targets[1] + 1))
-            tg = np.stack([rng.integers(max(1, n_samples // 25), n_samples - n_samples // 25, nt).astype(np.float64),
-                           rng.integers(0, n_chirps, nt).astype(np.float64),
-                           rng.uniform(amp[0], amp[1], nt)], axis=1)
-        truth.append(tg)
-        base = np.zeros((n_chirps, n_samples), dtype=np.complex128)
-        for (r, d, a) in tg:
-            base += a * np.exp(2j * np.pi * (r * s / n_samples + d * c / n_chirps))
-        ph = np.exp(1j * rng.uniform(0, 2 * np.pi, n_channels))[:, None, None]
-        x = base[None] * ph
-        x = x + sigma * (rng.standard_normal(x.shape) + 1j * rng.standard_normal(x.shape))
-        if dtype == "int16":
-            out.append(_quantise(x.real, x.imag))
-        else:
-            out.append(x.astype(np.complex64))
-    return np.stack(out), truth
+# BASELINE config 2 / 3 style cubes live with the product's scenario generator (inputs only); the tests reach them
+# through this module as before
+from fpga_fmcw_radar_processor_b200.scenario import synthetic_cube  # noqa: E402,F401

@@ -166,6 +166,22 @@ def case_cfar_signed_map(make_core, n_range=64, n_doppler=64, seed=5, **kw):
     assert int((ref["mag"] < 0).sum()) > 0                                             # negative detections exist and match
 
 
+def case_cfar_crowded_tile(make_core, n_range=64, n_doppler=128, seed=9, **kw):
+    """More surviving strips in one 64 x 64 tile than one phase-1 round takes (128) and more survivors than the
+    list holds at once: a lattice of strong isolated cells.  Bit-exact against the oracle."""
+    rng = np.random.default_rng(seed)
+    m = rng.rayleigh(40.0, size=(2, n_range, n_doppler)).astype(np.float32)
+    m[0, ::4, ::3] = rng.uniform(2000.0, 9000.0, size=m[0, ::4, ::3].shape).astype(np.float32)
+    m[1, ::2, ::2] *= 40.0
+    kw.setdefault("max_dets_per_cpi", 1 << 16)
+    with make_core(n_range=n_range, n_doppler=n_doppler, n_channels=2, **kw) as c:
+        dets, counts, status, dense = c.cfar_stage(m[None])
+    okw = {k: v for k, v in kw.items() if k in fp.DEFAULTS}
+    exp = np.stack([fp.cfar_stage(m[i], **okw) for i in range(2)])
+    assert np.array_equal(dense[0], exp)
+    assert counts[0] == np.count_nonzero(exp) and counts[0] > 300
+
+
 def case_end_to_end_mag_modes(make_core, n_ch=2, n_chirps=32, n_samples=64, seed=23):
     """Whole path with mag_mode pow and logpow (north_star: |X|^2 and the log magnitude), CFAR included, against the
     oracle -- once on an int16 cube (dB values far above 0) and once on a complex64 cube so weak that |X|^2 < 1
@@ -178,7 +194,7 @@ def case_end_to_end_mag_modes(make_core, n_ch=2, n_chirps=32, n_samples=64, seed
             cube = (cube * np.float32(scale)).astype(np.complex64)
         for mode in ("pow", "logpow"):
             with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, input_format=fmt, max_cpis=2,
-                           mag_mode=mode, max_dets_per_cpi=1 << 16) as c:
+                           mag_mode=mode, max_dets_per_cpi=n_ch * n_chirps * n_samples) as c:   # a dB map below 0 dB "detects" nearly everywhere
                 rd_map, dets, n_dets, status = (x.copy() for x in c.process(cube))
             ref_map, ref_dets, ref_counts = fp.process_batch(cube, mag_mode=mode)
             if mode == "logpow":

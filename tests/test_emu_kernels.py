@@ -67,6 +67,11 @@ def test_cfar_signed_map(make_core, nr, nd, kw):
     pc.case_cfar_signed_map(make_core, nr, nd, **kw)
 
 
+def test_cfar_crowded_tile(make_core):
+    pc.case_cfar_crowded_tile(make_core)
+    pc.case_cfar_crowded_tile(make_core, scale_override=2)
+
+
 def test_end_to_end_mag_modes(make_core):
     pc.case_end_to_end_mag_modes(make_core)
 

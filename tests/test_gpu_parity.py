@@ -88,6 +88,13 @@ def test_cfar_signed_map(make_core, nr, nd, kw):
     pc.case_cfar_signed_map(make_core, nr, nd, **kw)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(scale_override=2), dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2),
+                                dict(cfar_edges="raster")])
+def test_cfar_crowded_tile(make_core, kw):
+    pc.case_cfar_crowded_tile(make_core, **kw)
+    pc.case_cfar_crowded_tile(make_core, 512, 256, **kw)
+
+
 def test_end_to_end_mag_modes(make_core):
     """mag_mode pow / logpow through CFAR, int16 cube and a complex64 cube with |X|^2 < 1 (VERDICT r1 parity hole)."""
     pc.case_end_to_end_mag_modes(make_core)

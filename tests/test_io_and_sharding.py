@@ -110,3 +110,37 @@ def test_affinity_helpers_are_safe_without_a_gpu():
     before = os.sched_getaffinity(0)
     assert affinity.bind_to_gpu_numa_node(0) is None or isinstance(affinity.bind_to_gpu_numa_node(0), dict)
     assert os.sched_getaffinity(0) <= before
+
+
+def _socket_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    ex = rdp.SocketExchange(rank=rank, world=world)
+    try:
+        got = ex.all_gather((rank, bytes([rank]) * 64))              # the 64-byte IPC handles of the sharded mode
+        ex.barrier()
+        again = ex.all_gather(rank * 10)
+        q.put((rank, got, again))
+        ex.barrier()
+    finally:
+        ex.close()
+
+
+def test_socket_exchange_three_ranks():
+    """The torch-free rendezvous of the sharded mode (exchange.SocketExchange): all_gather + barrier, world 3."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port, world = _free_port(), 3
+    procs = [ctx.Process(target=_socket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, got, again in res:
+        assert got == [(r, bytes([r]) * 64) for r in range(world)] and again == [0, 10, 20]
+    one = rdp.SocketExchange(rank=0, world=1)
+    assert one.all_gather("x") == ["x"]
+    one.barrier()
