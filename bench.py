@@ -8,7 +8,11 @@ One "step" = one pass of the whole hot path (window -> range FFT -> corner turn 
 FFT -> magnitude -> 2D OS-CFAR -> sorted detection list) over the per-GPU batch of synthetic
 CPIs resident in HBM.  `value` = CPIs all ranks processed / max-over-ranks device time.
 `e2e` = the same metric through RadarCore.process() with pinned HOST buffers (H2D of the
-cube and D2H of the detection list inside the timed region).  Prints ONE JSON line on rank 0.
+cube and D2H of the detection list inside the timed region).  Prints ONE JSON line on rank 0
+(the LAST line of stdout; NCCL's own logging, if the caller enabled it, is left alone).
+With more than one GPU the line also carries `config4`: BASELINE config 4 (one 1024 x 4096 CPI
+sharded over the ranks, corner turn as K1 peer stores over NVLink), measured after the main
+region, with its parity against the single-GPU path computed on the box.
 """
 import argparse
 import json
@@ -103,8 +107,8 @@ class ClockSampler:
 
 
 def make_unique_cpis(n_unique, fmt):
-    from oracle import stimulus as st            # synthetic input generator only (not timed, not the product path)
-    cube, _ = st.synthetic_cube(n_unique, N_CH, N_CHIRPS, N_SAMPLES, seed=1234, dtype=fmt)
+    from fpga_fmcw_radar_processor_b200.scenario import synthetic_cube      # input generator (not timed)
+    cube, _ = synthetic_cube(n_unique, N_CH, N_CHIRPS, N_SAMPLES, seed=1234, dtype=fmt)
     return cube
 
 
@@ -134,10 +138,10 @@ def run_reference(args, rank, world):
     n_sample = procs                                   # one CPI (12 channels) per process per step
     cube = make_unique_cpis(min(n_sample, 4), args.fmt)
     cubes = [cube[i % cube.shape[0]] for i in range(n_sample)]
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     with mp.get_context("fork").Pool(procs) as pool:
-        for _ in range(max(1, min(args.warmup, 1))):
+        for _ in range(warmup):
             cpu_reference_step(cubes, pool)
-        steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(steps):
             cpu_reference_step(cubes, pool)
@@ -145,7 +149,7 @@ def run_reference(args, rank, world):
     value = n_sample * steps / dt
     sample = f"{n_sample} CPIs x {N_CH} ch per step over {procs} processes, {steps} steps (bounded sample of the batch)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": workload_name(args.fmt, args.cpis)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
@@ -164,7 +168,9 @@ def main():
     ap.add_argument("--fmt", default="int16", choices=["int16", "complex64"])
     ap.add_argument("--chunk", type=int, default=0, help="CPIs per internal pass (0 = auto, L2-sized)")
     ap.add_argument("--e2e-cpis", type=int, default=256)
-    ap.add_argument("--unique", type=int, default=8, help="distinct synthetic CPIs tiled over the batch")
+    ap.add_argument("--unique", type=int, default=64, help="distinct synthetic CPIs tiled over the batch")
+    ap.add_argument("--no-config4", action="store_true", help="skip the sharded large-CPI block (multi-GPU runs)")
+    ap.add_argument("--config4-cpis", type=int, default=32)
     ap.add_argument("--max-dets", type=int, default=131072, help="detection-list capacity per CPI")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -190,7 +196,6 @@ def main():
 
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: ONE JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -303,6 +308,54 @@ def main():
                "d2h_bytes_per_step": int(d2h), "cpis_per_step": ne, "steps": reps,
                "api": "RadarCore.process (rdp_process_host), pinned host buffers"}
 
+    # ---- what the host link can do at best: the same pinned buffer copied to the device, nothing else running, every
+    # rank at once (one cudaMemcpyAsync + sync per copy); e2e is judged against this ceiling, not against the kernels
+    if e2e is not None:
+        d_tmp = core.device_buffer(host.nbytes)
+        core._check(core.lib.rdp_copy_h2d(core.h, d_tmp.ptr, C.c_void_p(host.ctypes.data), host.nbytes))
+        barrier_max(0.0)
+        t0 = time.perf_counter()
+        n_copy = 5
+        for _ in range(n_copy):
+            core._check(core.lib.rdp_copy_h2d(core.h, d_tmp.ptr, C.c_void_p(host.ctypes.data), host.nbytes))
+        dt_copy = barrier_max((time.perf_counter() - t0) * 1e3)
+        d_tmp.free()
+        ceiling = world * n_copy * host.nbytes / (dt_copy * 1e-3) / 1e9
+        e2e["h2d_ceiling_gbs"] = ceiling
+        e2e["h2d_achieved_gbs"] = e2e["value"] * per_cpi / 1e9
+        e2e["frac_of_h2d_ceiling"] = e2e["h2d_achieved_gbs"] / ceiling
+        e2e["h2d_ceiling_note"] = ("aggregate over %d rank(s) of a plain pinned-host -> device copy loop of the same buffer, "
+                                   "all ranks concurrently" % world)
+
+    # ---- parity spot check on the box: one CPI of the TIMED batch (its records as the timed steps left them in
+    # device memory) against the CPU oracle on the same input
+    parity_spot = None
+    if rank == 0 and not args.no_cpu:
+        spot = min(n_cpi - 1, 5)
+        all_counts = d_cnt.download((n_cpi,), np.int32)
+        nd = int(min(all_counts[spot], core.max_dets_per_cpi))
+        got = d_dets.download((nd,), rdp.DET_DTYPE, offset=spot * core.max_dets_per_cpi * rdp.DET_DTYPE.itemsize)
+        from oracle import float_path as fp
+        src = uniq[spot % uniq.shape[0]]
+        with rdp.RadarCore(n_range=N_SAMPLES, n_doppler=N_CHIRPS, n_channels=N_CH, input_format=args.fmt, max_cpis=1,
+                           device=local_rank, max_dets_per_cpi=args.max_dets, **CFAR_KW) as c1:
+            gpu_map = c1.process(src[None])[0][0].copy()
+        ref_map, ref_dets = fp.process_cpi(src, **CFAR_KW)
+        peak = float(ref_map.max())
+        err = float(np.abs(gpu_map - ref_map).max())
+        eps = max(4.0 * err, 1e-7 * peak)
+        cells = lambda d: {(int(x["channel"]), int(x["range"]), int(x["doppler"])) for x in d}
+        diff = cells(got) ^ cells(ref_dets)
+        amb = {}
+        unexplained = 0
+        for (ch, r, d) in diff:
+            if ch not in amb:
+                amb[ch] = fp.ambiguous_cells(ref_map[ch], eps, **CFAR_KW)
+            unexplained += 0 if amb[ch][r, d] else 1
+        parity_spot = {"ok": bool(err <= 1e-4 * peak and unexplained == 0 and np.all(got["cpi"] == spot)), "cpi": spot,
+                       "map_err_of_peak": err / peak, "detections": int(nd), "oracle_detections": int(len(ref_dets)),
+                       "near_threshold_differences": len(diff), "unexplained_differences": unexplained}
+
     # ---- streaming ingest (BASELINE config 5): one CPI (12 channels) per submission from pinned host memory
     streaming = None
     if not args.no_e2e and not args.no_stream:
@@ -347,6 +400,22 @@ def main():
                "sample": f"{sample.shape[0]} CPIs x {N_CH} ch of the same workload through the NumPy oracle, one process "
                          f"(host has {os.cpu_count()} cores)"}
 
+    counts_mean, counts_max, status_or = float(counts.mean()), int(counts.max()), int(np.bitwise_or.reduce(status))
+    max_dets = int(core.max_dets_per_cpi)
+    cfar_tma = core.info()["cfar_tma"]
+    for b in (d_cube, d_dets, d_cnt, d_st):
+        b.free()
+    core.close()
+
+    # ---- BASELINE config 4 on the GPUs of this run (multi-GPU only; outside the timed region above)
+    config4 = None
+    if world > 1 and not args.no_config4:
+        try:
+            config4 = run_config4(rank, world, local_rank, barrier_max, args)
+        except Exception as e:                               # the headline stays valid; say why the block is missing
+            config4 = {"error": repr(e)[:300]}
+
+    line = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -355,17 +424,83 @@ def main():
                            "unique_cpis": int(uniq.shape[0]), "chunk_cpis": info["chunk_cpis"],
                            "cfar": ("ref 8/8 guard 4/2" if CFAR_KW else "ref 4/4 guard 2/1") + " rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
                            "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),
-                           "device": info["device_name"], "cfar_tile_staging": "TMA" if core.info()["cfar_tma"] else "manual", "sharding": "CPIs dealt to ranks, no data-path collective",
+                           "device": info["device_name"], "cfar_tile_staging": "TMA" if cfar_tma else "manual", "sharding": "CPIs dealt to ranks, no data-path collective",
                            "host_numa_binding": numa},
                 "clocks": clocks, "e2e": e2e, "streaming": streaming, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu,
-                "detections_per_cpi_mean": float(counts.mean()), "detections_per_cpi_max": int(counts.max()),
-                "max_dets_per_cpi": int(core.max_dets_per_cpi), "status_or": int(np.bitwise_or.reduce(status))}
-        print(json.dumps(line), flush=True)
-    core.close()
+                "cpu_baseline": cpu, "parity_spot": parity_spot, "config4": config4,
+                "detections_per_cpi_mean": counts_mean, "detections_per_cpi_max": counts_max,
+                "max_dets_per_cpi": max_dets, "status_or": status_or}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if line is not None:
+        sys.stderr.flush()
+        print(json.dumps(line), flush=True)                  # the last line of stdout
+
+
+def run_config4(rank, world, local_rank, barrier_max, args):
+    """BASELINE configs[3]: one 1024 x 4096 complex64 CPI with the wide CFAR, sharded over the ranks -- chirp-sharded
+    range FFT whose transposed store goes straight into the owning rank's memory over NVLink (CUDA IPC peer stores
+    from K1: the all-to-all corner turn without a collective), range-sharded Doppler FFT, CFAR with halo lines from
+    the neighbours.  Reports CPI/s, the NVLink rate while K1 runs, and parity with the single-GPU path computed HERE."""
+    import fpga_fmcw_radar_processor_b200 as rdp
+    from fpga_fmcw_radar_processor_b200.scenario import synthetic_cube
+    nc, ns, B, uniq = 1024, 4096, max(2, args.config4_cpis), 2
+    if nc % world or ns % world:
+        return {"skipped": "world size does not divide the CPI"}
+    kw = dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2)
+    cube, _ = synthetic_cube(uniq, 1, nc, ns, seed=404, dtype="complex64", n_targets=(3, 5), sigma=40.0)
+    cl = nc // world
+    local_cube = np.ascontiguousarray(cube[:, :, rank * cl:(rank + 1) * cl])
+    local_cube = np.concatenate([local_cube] * (B // uniq), axis=0)
+    B = local_cube.shape[0]
+    ex = rdp.SocketExchange(port_offset=11)
+    sh = rdp.ShardedCpi(n_chirps=nc, n_samples=ns, world=world, rank=rank, n_channels=1, n_cpi=B, input_format="complex64",
+                        device=local_rank, max_dets_per_cpi=1 << 14, **kw)
+    d_in = sh.upload_local(local_cube)
+    try:
+        for _ in range(2):
+            dets = sh.run_device(d_in, ex)
+        steps = 5
+        barrier_max(0.0)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            dets = sh.run_device(d_in, ex)           # every phase ends with a device sync and a barrier
+        dt = barrier_max((time.perf_counter() - t0) * 1e3) * 1e-3
+        ph = {}
+
+        def timed(name, fn):
+            a = time.perf_counter()
+            fn()                                     # the phase methods synchronise their device work
+            ph[name] = (time.perf_counter() - a) * 1e3
+        timed("range_scatter", lambda: sh.range_scatter_device(d_in)); ex.barrier()
+        timed("doppler", sh.doppler); ex.barrier()
+        timed("halo", sh.halo_exchange)
+        timed("cfar", sh.cfar); ex.barrier()
+        # parity on the box: this rank's range lines of the map and its detections against the single-GPU path
+        local_map = sh.local_map()[:uniq]
+        with rdp.RadarCore(n_range=ns, n_doppler=nc, n_channels=1, input_format="complex64", max_cpis=uniq,
+                           max_dets_per_cpi=1 << 16, device=local_rank, **kw) as c:
+            ref_map, ref_dets = (x.copy() for x in c.process(cube)[:2])
+        rows = ns // world
+        mine = ref_dets[(ref_dets["range"] >= rank * rows) & (ref_dets["range"] < (rank + 1) * rows)]
+        got = dets[dets["cpi"] < uniq]
+        ok = bool(np.array_equal(local_map, ref_map[:, :, rank * rows:(rank + 1) * rows]) and len(got) == len(mine) and
+                  all(np.array_equal(got[f], mine[f]) for f in ("cpi", "channel", "range", "doppler", "mag")))
+        oks = ex.all_gather((ok, int(len(got)), int(len(dets))))
+    finally:
+        d_in.free()
+        sh.close()
+        ex.close()
+    cpis = B * steps / dt
+    a2a_bytes = nc * ns * 8 * (world - 1) / world               # bytes of one CPI that cross NVLink in the corner turn
+    return {"workload": f"large_{nc}x{ns}x1ch_complex64_sharded_cpi", "cfar": "ref 8/8 guard 4/2 (N_REF 480)",
+            "value": cpis, "unit": UNIT, "cpis_per_step": B, "steps": steps, "ms_per_step": dt / steps * 1e3, "scaling": "strong",
+            "parity_vs_single_gpu": bool(all(o[0] for o in oks)), "detections_checked": int(sum(o[1] for o in oks)),
+            "all_to_all": {"bytes_per_cpi": a2a_bytes, "gbs_sustained": a2a_bytes * cpis / 1e9,
+                           "nvlink_gbs_per_gpu_during_k1": (a2a_bytes / world) * B / (ph["range_scatter"] * 1e-3) / 1e9},
+            "phase_ms_rank0": ph,
+            "how": "corner turn = K1 peer stores over NVLink (CUDA IPC), no collective; barriers + IPC handles over TCP sockets"}
 
 
 if __name__ == "__main__":

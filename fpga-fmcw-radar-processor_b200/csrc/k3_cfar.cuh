@@ -167,10 +167,14 @@ __device__ __forceinline__ bool cfar_exact_warp(const CfarArgs& a, FETCH fetch, 
 // Tiled kernel, geometry compile-time.  CTA = TR / 8 warps; tile = TR range lines x 64 Doppler
 // columns; warp = one band of 8 lines, lane = two adjacent columns.
 // ------------------------------------------------------------------------------------------
-template <int HL, int HC, int GL, int GC, int TR_, int NSTAGE_>
+template <int HL, int HC, int GL, int GC, int TR_, int NSTAGE_, int P0B_ = 1>
 struct K3Shape {
     static constexpr int S = 8, TC = 64, TR = TR_, NSTAGE = NSTAGE_;
     static constexpr int NBAND = TR / S, NWARP = NBAND, THREADS = 32 * NWARP;
+    // phase 0: a thread owns P0B vertically adjacent bands (x 2 columns); with P0B = 2 only half of the warps run it,
+    // but every 128-bit load of a column serves two strips more -- phase 0 is bound by shared-memory bandwidth
+    static constexpr int P0B = P0B_;
+    static_assert(NBAND % P0B_ == 0, "bands per phase-0 thread");
     // TMA needs the box to START on a 16-byte boundary in the innermost dimension (an unaligned start
     // coordinate traps with "illegal instruction", tools/microbench/mb_tma_probe.cu), so the column halo is
     // padded to a multiple of 4 floats on both sides: tile column c sits at staged column c + HCP
@@ -186,7 +190,9 @@ struct K3Shape {
     static constexpr int NP = S / 2 + HL;                         // row pairs under one strip (its support)
     static constexpr int NPL = (NP + 3) / 4;                      // 128-bit loads per column
     static constexpr int PAIRS = SRP / 2;
-    static constexpr int PITCH_MIN = PAIRS > (NBAND - 1) * (S / 2) + 4 * NPL ? PAIRS : (NBAND - 1) * (S / 2) + 4 * NPL;
+    static constexpr int NP0 = NP + (S / 2) * (P0B - 1), NPL0 = (NP0 + 3) / 4;   // row pairs / 128-bit loads per column in phase 0
+    static constexpr int LAST_READ = ((NBAND - 1) * (S / 2) + 4 * NPL > (NBAND - P0B) * (S / 2) + 4 * NPL0) ? (NBAND - 1) * (S / 2) + 4 * NPL : (NBAND - P0B) * (S / 2) + 4 * NPL0;
+    static constexpr int PITCH_MIN = PAIRS > LAST_READ ? PAIRS : LAST_READ;
     // consecutive lanes read consecutive columns of one plane with 128-bit loads: the 8 lanes of a quarter-warp
     // cover all 32 banks iff the pitch is 4 mod 8 words
     static constexpr int PITCH = PITCH_MIN + ((12 - PITCH_MIN % 8) % 8);
@@ -215,6 +221,7 @@ struct K3Shape {
     static constexpr int occupancy_hint() {                        // CTAs per SM the shared memory allows (<= 2048 threads)
         int n = (int)((227 * 1024) / (smem_bytes() + 1024));
         if (n > 2048 / THREADS) n = 2048 / THREADS;
+        if (P0B > 1 && n > 3) n = 3;                                  // the wider phase 0 wants ~80 registers
         return n < 1 ? 1 : n;
     }
 };
@@ -307,12 +314,12 @@ __device__ __forceinline__ bool k3_strip_reaches(const uint32_t (&P)[NP], int ne
     return f;
 }
 
-template <int HL, int HC, int GL, int GC, int TR, int NSTAGE, bool INT_MODE>
-__global__ void __launch_bounds__((K3Shape<HL, HC, GL, GC, TR, NSTAGE>::THREADS), (K3Shape<HL, HC, GL, GC, TR, NSTAGE>::occupancy_hint()))
+template <int HL, int HC, int GL, int GC, int TR, int NSTAGE, int P0B, bool INT_MODE>
+__global__ void __launch_bounds__((K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>::THREADS), (K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>::occupancy_hint()))
 k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, uint32_t* __restrict__ det_bits,
                CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
                const RDP_GRID_CONSTANT CUtensorMap tmap) {
-    using Sh = K3Shape<HL, HC, GL, GC, TR, NSTAGE>;
+    using Sh = K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>;
     constexpr int S = Sh::S, TC = Sh::TC, SC = Sh::SC, SR = Sh::SR, SRP = Sh::SRP, HCP = Sh::HCP, NG = Sh::NG;
     constexpr int NP = Sh::NP, NPL = Sh::NPL, PITCH = Sh::PITCH, PLANE = Sh::PLANE, THREADS = Sh::THREADS, NWARP = Sh::NWARP;
     RDP_DYN_SMEM(smem_raw);
@@ -509,71 +516,88 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
 
     if (!signed_tile) {
     // ---- phase 0: one shared threshold per strip ------------------------------------------------------------
-    if (!(a.debug_skip & 2)) {
-        const int b = warp;                                        // band: tile lines 8 b .. 8 b + 7, staged rows 8 b .. 8 b + 7 + 2 HL
+    if (!(a.debug_skip & 2) && warp < NWARP / P0B) {
+        constexpr int NP0 = Sh::NP0, NPL0 = Sh::NPL0;
+        const int b0 = P0B * warp;                                 // bands b0 .. b0 + P0B - 1: tile lines 8 b0 .., staged rows 8 b0 .. 8 (b0 + P0B) - 1 + 2 HL
         const int s0 = 2 * lane + HCP;                             // staged column of the first of this lane's two columns
-        float cm0 = 0.0f, cm1 = 0.0f;                              // largest cut of either strip
+        uint32_t td[P0B][2];                                       // strip thresholds (band, column), duplicated into both halves
+        bool tiny[P0B][2];
         RDP_UNROLL
-        for (int j = 0; j < S; ++j) {
-            const float2 c2 = *reinterpret_cast<const float2*>(tf + (S * b + HL + j) * SC + s0);
-            cm0 = fmaxf(cm0, cfar_word_as_float<INT_MODE>(c2.x));
-            cm1 = fmaxf(cm1, cfar_word_as_float<INT_MODE>(c2.y));
-        }
-        float lo_b = 0.0f;                                         // pf_c x the largest window-sum bound of the strip's cells
-        if (a.adaptive) {
-            const float* gp = cov + (S * b) * NG + ((s0 - HC) >> 2);
-            float x[S + 2 * HL];
+        for (int bb = 0; bb < P0B; ++bb) {
+            float cm0 = 0.0f, cm1 = 0.0f;                          // largest cut of either strip
             RDP_UNROLL
-            for (int k = 0; k < S + 2 * HL; ++k) x[k] = gp[k * NG];
-            float wsum[S];
-            k3_window_sums<HL, S>(x, a.pf_c, wsum);
-            lo_b = wsum[0];
-            RDP_UNROLL
-            for (int j = 1; j < S; ++j) lo_b = fmaxf(lo_b, wsum[j]);
+            for (int j = 0; j < S; ++j) {
+                const float2 c2 = *reinterpret_cast<const float2*>(tf + (S * (b0 + bb) + HL + j) * SC + s0);
+                cm0 = fmaxf(cm0, cfar_word_as_float<INT_MODE>(c2.x));
+                cm1 = fmaxf(cm1, cfar_word_as_float<INT_MODE>(c2.y));
+            }
+            float lo_b = 0.0f;                                     // pf_c x the largest window-sum bound of the strip's cells
+            if (a.adaptive) {
+                const float* gp = cov + (S * (b0 + bb)) * NG + ((s0 - HC) >> 2);
+                float x[S + 2 * HL];
+                RDP_UNROLL
+                for (int k = 0; k < S + 2 * HL; ++k) x[k] = gp[k * NG];
+                float wsum[S];
+                k3_window_sums<HL, S>(x, a.pf_c, wsum);
+                lo_b = wsum[0];
+                RDP_UNROLL
+                for (int j = 1; j < S; ++j) lo_b = fmaxf(lo_b, wsum[j]);
+            }
+            const uint32_t h0 = bf16_up(fmaxf(cm0 * a.pf_a, fminf(cm0 * a.pf_b, lo_b)));
+            const uint32_t h1 = bf16_up(fmaxf(cm1 * a.pf_a, fminf(cm1 * a.pf_b, lo_b)));
+            td[bb][0] = h0 | (h0 << 16);
+            td[bb][1] = h1 | (h1 << 16);
+            tiny[bb][0] = cfar_tiny_cut(cm0);
+            tiny[bb][1] = cfar_tiny_cut(cm1);
         }
-        const float t0 = fmaxf(cm0 * a.pf_a, fminf(cm0 * a.pf_b, lo_b));
-        const float t1 = fmaxf(cm1 * a.pf_a, fminf(cm1 * a.pf_b, lo_b));
-        const uint32_t h0 = bf16_up(t0), h1 = bf16_up(t1);
-        const uint32_t td0 = h0 | (h0 << 16), td1 = h1 | (h1 << 16);
-        uint32_t acc0[NP], acc1[NP];
+        uint32_t acc[P0B][2][NP];
         RDP_UNROLL
-        for (int i = 0; i < NP; ++i) { acc0[i] = 0u; acc1[i] = 0u; }
-        const uint32_t* pl = planes + (S / 2) * b + lane * PITCH;
+        for (int bb = 0; bb < P0B; ++bb)
+            RDP_UNROLL
+            for (int i = 0; i < NP; ++i) { acc[bb][0][i] = 0u; acc[bb][1][i] = 0u; }
+        const uint32_t* pl = planes + (S / 2) * b0 + lane * PITCH;
         RDP_UNROLL
         for (int k = 0; k <= 2 * HC + 1; ++k) {                    // staged column s0 - HC + k: parity and plane position are compile-time
             const uint4* src = reinterpret_cast<const uint4*>(pl + ((HC + k) & 1) * PLANE + ((HCP - HC + k) >> 1) * PITCH);
-            uint32_t w[4 * NPL];
+            uint32_t w[4 * NPL0];
             RDP_UNROLL
-            for (int v = 0; v < NPL; ++v) {
+            for (int v = 0; v < NPL0; ++v) {
                 const uint4 u = src[v];
                 w[4 * v] = u.x; w[4 * v + 1] = u.y; w[4 * v + 2] = u.z; w[4 * v + 3] = u.w;
             }
-            if (k <= 2 * HC) {
-                RDP_UNROLL
-                for (int i = 0; i < NP; ++i) acc0[i] -= bf16x2_lt_mask(w[i], td0);
-            }
-            if (k >= 1) {
-                RDP_UNROLL
-                for (int i = 0; i < NP; ++i) acc1[i] -= bf16x2_lt_mask(w[i], td1);
+            RDP_UNROLL
+            for (int bb = 0; bb < P0B; ++bb) {                     // band bb sees the pairs (S / 2) bb .. (S / 2) bb + NP - 1 of this load
+                if (k <= 2 * HC) {
+                    RDP_UNROLL
+                    for (int i = 0; i < NP; ++i) acc[bb][0][i] -= bf16x2_lt_mask(w[(S / 2) * bb + i], td[bb][0]);
+                }
+                if (k >= 1) {
+                    RDP_UNROLL
+                    for (int i = 0; i < NP; ++i) acc[bb][1][i] -= bf16x2_lt_mask(w[(S / 2) * bb + i], td[bb][1]);
+                }
             }
         }
-        const bool f0 = k3_strip_reaches<HL, NP>(acc0, need) || cfar_tiny_cut(cm0);
-        const bool f1 = k3_strip_reaches<HL, NP>(acc1, need) || cfar_tiny_cut(cm1);
-        const uint32_t b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
-        const int n0 = __popc(b0), n1 = __popc(b1);
-        if (n0 + n1) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(n_strips_ctr, n0 + n1);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t below = (1u << lane) - 1u;
-            if (f0) strips[base + __popc(b0 & below)] = (unsigned short)(b * TC + 2 * lane);
-            if (f1) strips[base + n0 + __popc(b1 & below)] = (unsigned short)(b * TC + 2 * lane + 1);
+        static_assert(NP0 <= 4 * NPL0, "phase-0 loads");
+        RDP_UNROLL
+        for (int bb = 0; bb < P0B; ++bb) {
+            const bool f0 = k3_strip_reaches<HL, NP>(acc[bb][0], need) || tiny[bb][0];
+            const bool f1 = k3_strip_reaches<HL, NP>(acc[bb][1], need) || tiny[bb][1];
+            const uint32_t m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+            const int n0 = __popc(m0), n1 = __popc(m1);
+            if (n0 + n1) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(n_strips_ctr, n0 + n1);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t below = (1u << lane) - 1u;
+                if (f0) strips[base + __popc(m0 & below)] = (unsigned short)((b0 + bb) * TC + 2 * lane);
+                if (f1) strips[base + n0 + __popc(m1 & below)] = (unsigned short)((b0 + bb) * TC + 2 * lane + 1);
+            }
         }
         if (cfar_out && c0 + 2 * lane < a.n_doppler) {             // dense output: zero everywhere, phase 2 writes the detections
             RDP_UNROLL
-            for (int j = 0; j < S; ++j)
-                if (r0 + S * b + j < a.n_range)
-                    *reinterpret_cast<float2*>(cfar_out + out_base + (long long)(r0 + S * b + j) * a.n_doppler + c0 + 2 * lane) = make_float2(0.0f, 0.0f);
+            for (int j = 0; j < P0B * S; ++j)
+                if (r0 + S * b0 + j < a.n_range)
+                    *reinterpret_cast<float2*>(cfar_out + out_base + (long long)(r0 + S * b0 + j) * a.n_doppler + c0 + 2 * lane) = make_float2(0.0f, 0.0f);
         }
     }
     __syncthreads();

@@ -210,22 +210,22 @@ bool k2_for(int n, K2Launcher* out) {
 }
 
 // ---- K3 dispatch ---------------------------------------------------------------------------
-template <int HL, int HC, int GL, int GC, int TR, int NSTAGE>
+template <int HL, int HC, int GL, int GC, int TR, int NSTAGE, int P0B = 1>
 struct K3Inst {
-    using Sh = K3Shape<HL, HC, GL, GC, TR, NSTAGE>;
+    using Sh = K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>;
     static cudaError_t prepare(size_t s, int* occ) {
-        cudaError_t e = prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, true>, Sh::THREADS, s, nullptr);
+        cudaError_t e = prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, P0B, true>, Sh::THREADS, s, nullptr);
         if (e != cudaSuccess) return e;
-        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, false>, Sh::THREADS, s, occ);
+        return prepare_kernel(k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, P0B, false>, Sh::THREADS, s, occ);
     }
     static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out,
                        uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
                        const CUtensorMap* tmap) {
         if (a.int_mode)
-            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, true>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
+            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, P0B, true>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
                        det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
         else
-            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, false>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
+            RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, P0B, false>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
                        det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
     }
     static K3Launcher get() {
@@ -245,13 +245,16 @@ struct K3Generic {
 };
 
 // `variant` (RDP_K3_VARIANT, A/B measurements of the default window only): 0 = 64-line tiles, one raw stage;
-// 1 = 64 lines, two stages; 2 = 32 lines, one stage; 3 = 32 lines, two stages
+// 1 = 64 lines, two stages; 2 = 32 lines, one stage; 3 = 32 lines, two stages; 4 / 5 = 64 lines, two / one stage(s),
+// phase 0 with two bands per thread on half of the warps
 K3Launcher k3_for(int hl, int hc, int gl, int gc, int variant) {
 #define RDP_K3_CASE(HL, HC, GL, GC, TR, NS) \
     if (hl == HL && hc == HC && gl == GL && gc == GC) return K3Inst<HL, HC, GL, GC, TR, NS>::get();
     if (variant == 1) { RDP_K3_CASE(5, 6, 1, 2, 64, 2) }
     if (variant == 2) { RDP_K3_CASE(5, 6, 1, 2, 32, 1) }
     if (variant == 3) { RDP_K3_CASE(5, 6, 1, 2, 32, 2) }
+    if (variant == 4 && hl == 5 && hc == 6 && gl == 1 && gc == 2) return K3Inst<5, 6, 1, 2, 64, 2, 2>::get();
+    if (variant == 5 && hl == 5 && hc == 6 && gl == 1 && gc == 2) return K3Inst<5, 6, 1, 2, 64, 1, 2>::get();
     RDP_K3_CASE(5, 6, 1, 2, 64, 1)      // radar_core.vhd:376-382 defaults (4,4,2,1), as built
     RDP_K3_CASE(6, 5, 2, 1, 64, 1)      // same, as named
     RDP_K3_CASE(3, 4, 1, 1, 64, 1)      // tb_os_cfar_2d.vhd:16-19 (3,2,1,1), as built
