@@ -63,6 +63,7 @@ struct CfarArgs {
     // pre-filter threshold: T = max(cut * pf_a, min(cut * pf_b, window_sum * pf_c))
     // (non-adaptive: pf_a = 1.001 / s1, pf_b = pf_c = 0)
     float pf_a, pf_b, pf_c;
+    int neg1;                               // -1 (an opaque multiplier: see k3_count)
     int skew_div;                           // CTAs per residency slot (= SM count)
     int skew_ns;                            // RDP_K3_SKEW_NS: start-up skew between the CTAs that share an SM (see the kernel)
     int debug_skip;                         // RDP_K3_DEBUG_SKIP (timing experiments only; results are WRONG when set): 1 = no phases 1 / 2, 2 = no phase 0, 4 = no conversion
@@ -102,6 +103,20 @@ __device__ __forceinline__ uint32_t bf16x2_lt_mask(uint32_t a, uint32_t b) {
     uint32_t r;
     asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
+#endif
+}
+// acc -= mask on the FMA pipe (IMAD: mask * -1 + acc).  The packed compares and most of the bookkeeping around them
+// run on the ALU pipe, which is the busier one in phases 0 and 1; RDP_K3_IMAD=0 at build time keeps plain subtractions.
+#ifndef RDP_K3_IMAD
+#define RDP_K3_IMAD 1
+#endif
+// (`neg1` is -1 handed in as a kernel argument: with a literal the assembler turns the multiply-add back into IADD3)
+__device__ __forceinline__ void k3_count(uint32_t& acc, uint32_t mask, uint32_t neg1) {
+#if defined(RDP_EMU) || !RDP_K3_IMAD
+    (void)neg1;
+    acc -= mask;
+#else
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(mask), "r"(neg1));
 #endif
 }
 // two floats (>= 0) -> their bfloat16 truncations, `a` in the low half and `b` in the high half
@@ -337,6 +352,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     const int tiles_per_map = tiles_r * tiles_c;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int need = a.rank_idx + 1;
+    const uint32_t neg1 = (uint32_t)a.neg1;
 
     // the zero cell behind every raw stage is never written again
     for (int st = 0; st < NSTAGE; ++st)
@@ -569,11 +585,11 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             for (int bb = 0; bb < P0B; ++bb) {                     // band bb sees the pairs (S / 2) bb .. (S / 2) bb + NP - 1 of this load
                 if (k <= 2 * HC) {
                     RDP_UNROLL
-                    for (int i = 0; i < NP; ++i) acc[bb][0][i] -= bf16x2_lt_mask(w[(S / 2) * bb + i], td[bb][0]);
+                    for (int i = 0; i < NP; ++i) k3_count(acc[bb][0][i], bf16x2_lt_mask(w[(S / 2) * bb + i], td[bb][0]), neg1);
                 }
                 if (k >= 1) {
                     RDP_UNROLL
-                    for (int i = 0; i < NP; ++i) acc[bb][1][i] -= bf16x2_lt_mask(w[(S / 2) * bb + i], td[bb][1]);
+                    for (int i = 0; i < NP; ++i) k3_count(acc[bb][1][i], bf16x2_lt_mask(w[(S / 2) * bb + i], td[bb][1]), neg1);
                 }
             }
         }
@@ -651,7 +667,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                 }
                 const bool guard_col = kk - HC >= -GC && kk - HC <= GC;
                 RDP_UNROLL
-                for (int i = 0; i < NP; ++i) acc -= bf16x2_lt_mask(w[i], guard_col ? opg[i] : opn[i]);
+                for (int i = 0; i < NP; ++i) k3_count(acc, bf16x2_lt_mask(w[i], guard_col ? opg[i] : opn[i]), neg1);
             }
             const bool keep = ((int)(k3_lo_count(acc) + k3_hi_count(acc)) >= need || cfar_tiny_cut(cut)) &&
                               c0 + tx < a.n_doppler && r0 + S * b + j < a.n_range;
@@ -705,9 +721,9 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                         const int ra = 2 * i, rb = 2 * i + 1;
                         const bool in_a = ra >= j && ra <= j + 2 * HL && !(guard_col && ra >= j + HL - GL && ra <= j + HL + GL);
                         const bool in_b = rb >= j && rb <= j + 2 * HL && !(guard_col && rb >= j + HL - GL && rb <= j + HL + GL);
-                        if (in_a && in_b) acc[j] -= bf16x2_lt_mask(w[i], td[j]);
-                        else if (in_a) acc[j] -= bf16x2_lt_mask(w[i], tl[j]);
-                        else if (in_b) acc[j] -= bf16x2_lt_mask(w[i], th[j]);
+                        if (in_a && in_b) k3_count(acc[j], bf16x2_lt_mask(w[i], td[j]), neg1);
+                        else if (in_a) k3_count(acc[j], bf16x2_lt_mask(w[i], tl[j]), neg1);
+                        else if (in_b) k3_count(acc[j], bf16x2_lt_mask(w[i], th[j]), neg1);
                     }
                 }
             }

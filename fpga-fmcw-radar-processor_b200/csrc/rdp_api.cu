@@ -290,6 +290,7 @@ struct rdp_handle {
     int device = 0;
     int sm_count = 0;
     int chunk = 1;
+    int host_chunk = 1;            // CPIs per pass of rdp_process_host (<= chunk)
     cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaStream_t cfar_stream = nullptr;    // overlap mode: K3/K4 of chunk i run here while K1/K2 of chunk i+1 run on `stream`
     cudaStream_t cur = nullptr;            // stream the run_* helpers launch on
@@ -743,6 +744,7 @@ int init_handle(rdp_handle* h) {
     a.raster = c.cfar_edges == RDP_EDGES_RASTER;
     a.int_mode = 0;
     a.debug_skip = h->knob_k3_debug_skip;
+    a.neg1 = -1;
     a.skew_ns = h->knob_k3_skew_ns;
     a.skew_div = h->sm_count > 0 ? h->sm_count : 1;
     a.is1 = (int)a.s1; a.ismin = c.scale_min; a.isnom = c.scale_nom; a.ismax = c.scale_max;
@@ -768,20 +770,24 @@ int init_handle(rdp_handle* h) {
     }
 #endif
 
-    // chunking: keep the range-major intermediate of one chunk L2-resident between K1 and K2
+    // chunking.  Measured on B200 (profiles/r2_summary.md): every launch costs ~12-15 us of ramp-up and tail on top of
+    // its work, so a pass over few CPIs loses more than an L2-resident intermediate would save; with the automotive
+    // shape the device-resident path is flat from 128 CPIs per chunk (1.5 GiB of range-major intermediate) up and 6 %
+    // slower at 32.  The HOST path moves its chunks through PCIe while the previous one is computed, so it wants
+    // SHORT chunks (the last one's kernels are exposed): it walks the same scratch in sub-chunks of <= 384 MiB.
     const size_t xrc_per_cpi = cells_per_cpi(c) * sizeof(float2);
     int chunk = c.chunk_cpis;
     if (chunk == 0) {
-        // measured on B200 (profiles/r1_summary.md): launches of a few CPIs are dominated by ramp / tail
-        // effects, which cost more than keeping the intermediate L2-resident saves; with the two-stream
-        // overlap of CFAR and FFT kernels the best chunk is ~32 automotive CPIs = 384 MiB of intermediate.
-        size_t budget = (size_t)384 << 20;
+        size_t budget = (size_t)1536 << 20;
         chunk = (int)(budget / xrc_per_cpi);
         if (chunk < 1) chunk = 1;
         if (chunk > 256) chunk = 256;
     }
     if (chunk > c.max_cpis) chunk = c.max_cpis;
     h->chunk = chunk;
+    h->host_chunk = (int)(((size_t)384 << 20) / xrc_per_cpi);
+    if (h->host_chunk < 1) h->host_chunk = 1;
+    if (h->host_chunk > chunk || c.chunk_cpis != 0) h->host_chunk = chunk;   // an explicit chunk_cpis is honoured as given
     rc = dev_alloc(h, &h->x_rc, (size_t)chunk * cells_per_cpi(c));
     if (rc) return rc;
     for (int i = 0; i < 2; ++i) {
@@ -1036,8 +1042,8 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
         return RDP_OK;
     };
     int k = 0, prev_base = 0, prev_n = 0;
-    for (int base = 0; base < n_cpi; base += h->chunk, ++k) {
-        const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
+    for (int base = 0; base < n_cpi; base += h->host_chunk, ++k) {
+        const int n = (n_cpi - base) < h->host_chunk ? (n_cpi - base) : h->host_chunk;
         const int b = k & 1;
         // H2D of chunk k on the copy stream, once the kernels that read this staging buffer (chunk k-2) are done
         if (k >= 2) RDP_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));

@@ -166,6 +166,28 @@ def case_cfar_signed_map(make_core, n_range=64, n_doppler=64, seed=5, **kw):
     assert int((ref["mag"] < 0).sum()) > 0                                             # negative detections exist and match
 
 
+def case_cfar_tiny_magnitudes(make_core, n_range=64, n_doppler=64, seed=13, **kw):
+    """Magnitudes in the bfloat16 / float32 SUBNORMAL range and below bfloat16 resolution (< 9.2e-41): the packed
+    pre-filters work on bfloat16 truncations (which honour subnormals, tools/microbench/mb_bf16_subnormal.cu) and
+    take their cuts from them; truncations of 0 fall back to the exact words.  Bit-exact against the oracle."""
+    rng = np.random.default_rng(seed)
+    m = np.zeros((2, n_range, n_doppler), np.float32)
+    m[0] = (rng.rayleigh(60.0, size=(n_range, n_doppler)) * 1e-41).astype(np.float32)     # ~6e-40: subnormal everywhere
+    m[0, 20, 30] = np.float32(5e-38)
+    m[0, 21, 30] = np.float32(2e-38)
+    m[0, 40, 5] = np.float32(3e-39)
+    m[1, 10, 10] = np.float32(3e-44)                                  # below bfloat16 resolution, alone among zeros: a detection
+    m[1, 30:34, 40:44] = np.float32(1.4e-45)                          # the smallest float32 magnitudes
+    m[1, 50, 20] = np.float32(7.0)                                    # and an ordinary cell on the same map
+    kw.setdefault("max_dets_per_cpi", 1 << 14)
+    with make_core(n_range=n_range, n_doppler=n_doppler, n_channels=2, **kw) as c:
+        dets, counts, status, dense = c.cfar_stage(m[None])
+    okw = {k: v for k, v in kw.items() if k in fp.DEFAULTS}
+    exp = np.stack([fp.cfar_stage(m[i], **okw) for i in range(2)])
+    assert np.array_equal(dense[0], exp)
+    assert counts[0] == np.count_nonzero(exp) and exp[1, 10, 10] != 0 and exp[0, 20, 30] != 0
+
+
 def case_cfar_crowded_tile(make_core, n_range=64, n_doppler=128, seed=9, **kw):
     """More surviving strips in one 64 x 64 tile than one phase-1 round takes (128) and more survivors than the
     list holds at once: a lattice of strong isolated cells.  Bit-exact against the oracle."""

@@ -67,6 +67,11 @@ def test_cfar_signed_map(make_core, nr, nd, kw):
     pc.case_cfar_signed_map(make_core, nr, nd, **kw)
 
 
+def test_cfar_tiny_magnitudes(make_core):
+    pc.case_cfar_tiny_magnitudes(make_core)
+    pc.case_cfar_tiny_magnitudes(make_core, scale_override=3, cfar_edges="raster")
+
+
 def test_cfar_crowded_tile(make_core):
     pc.case_cfar_crowded_tile(make_core)
     pc.case_cfar_crowded_tile(make_core, scale_override=2)

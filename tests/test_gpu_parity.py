@@ -88,6 +88,13 @@ def test_cfar_signed_map(make_core, nr, nd, kw):
     pc.case_cfar_signed_map(make_core, nr, nd, **kw)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(scale_override=3, cfar_edges="raster"), dict(cfar_axes="as_named"),
+                                dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2)])
+def test_cfar_tiny_magnitudes(make_core, kw):
+    pc.case_cfar_tiny_magnitudes(make_core, **kw)
+    pc.case_cfar_tiny_magnitudes(make_core, 256, 128, **kw)
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(scale_override=2), dict(cfar_ref_r=8, cfar_ref_d=8, cfar_guard_r=4, cfar_guard_d=2),
                                 dict(cfar_edges="raster")])
 def test_cfar_crowded_tile(make_core, kw):
