@@ -7,6 +7,11 @@
 // range-major ([range][chirp], corner_turner.vhd:79-80) as TC*8-byte contiguous segments,
 // so the transpose costs no extra pass over HBM.
 //   algorithmic HBM bytes / cell: B_in (4 int16-IQ | 8 complex64) read + 8 written.
+// With 16-chirp tiles the tile goes out as TMA stores (cp.async.bulk.tensor, SASS UTMASTG): the spectra are written
+// into a dense [range][16 chirps] box in the tensor map's 128-byte swizzle (the XOR of the 16-byte chunk index with
+// the row keeps the column writes of the FFT epilogue spread over the banks), one elected thread issues the
+// 256-row boxes, and the CTA is already transforming the next tile while the TMA unit drains this one -- no store loop,
+// no second pass of the tile through the LSU.
 //
 // Long chirps (2048 / 4096 samples) leave room for only 8 / 4 chirps of a tile in one SM's shared memory, i.e.
 // 64- / 32-byte output segments.  For those the kernel runs as thread-block CLUSTERS of CS = 2 / 4 CTAs: each
@@ -27,8 +32,9 @@ struct K1Shape {
     // chirps per tile: 128-byte output segments (16 x complex64) unless shared memory forbids
     static constexpr int TC_MAX = (Plan::N <= 1024) ? (G > 16 ? G : 16) : (Plan::N == 2048 ? 8 : 4);
     static __host__ __device__ constexpr size_t smem_bytes(int tile_chirps) {
-        return sizeof(float2) * ((size_t)Plan::N * (tile_chirps + 1) + (size_t)G * Plan::XBUFS);
+        return sizeof(float2) * ((size_t)Plan::N * (tile_chirps + 1) + (size_t)G * Plan::XBUFS) + 1024;   // + slack: the tile starts on a 1 KiB boundary (swizzle atom)
     }
+    static constexpr int BOX_ROWS = Plan::N < 256 ? Plan::N : 256;    // range lines per TMA store box
     // cluster variant: CS CTAs, each holding N / CS range bins of CS * TC_MAX chirps
     static constexpr int CS = (Plan::N == 4096) ? 4 : (Plan::N == 2048 ? 2 : 1);
     static constexpr int CL_ROWS = Plan::N / CS, CL_COLS = CS * TC_MAX, CL_PITCH = CL_COLS + 1;
@@ -96,14 +102,17 @@ template <class Plan, int IN_FMT>
 __global__ void __launch_bounds__(K1Shape<Plan>::THREADS)
 k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
                 const float* __restrict__ window, const float2* __restrict__ twtab,
-                int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc) {
+                int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc,
+                int use_tma_store, const RDP_GRID_CONSTANT CUtensorMap tmap_out) {
     constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
     constexpr int G = K1Shape<Plan>::G, THREADS = K1Shape<Plan>::THREADS, TCM = K1Shape<Plan>::TC_MAX;
     using P0 = typename Plan::P0;
     using PL = typename Plan::LAST;
     using Raw = K1Raw<IN_FMT>;
     RDP_DYN_SMEM(smem_raw);
-    float2* tile = reinterpret_cast<float2*>(smem_raw);
+    float2* tile = reinterpret_cast<float2*>(smem_raw + ((1024 - ((uintptr_t)smem_raw & 1023)) & 1023));
+    unsigned char* const tile_bytes = reinterpret_cast<unsigned char*>(tile);
+    bool store_pending = false;                            // a TMA store of the previous tile may still be reading the box
     const int tcp = tile_chirps + 1;                       // +1 complex: conflict-free column writes
     float2* xbuf = tile + (size_t)N * tcp + (size_t)(threadIdx.x / T) * Plan::XBUFS;
     const int tid = threadIdx.x % T, gid = threadIdx.x / T;
@@ -169,6 +178,25 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
             if (it + 1 < iters) fetch(t, it + 1);
             else fetch(t + (int)gridDim.x, 0);
             Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
+#ifndef RDP_EMU
+            if (use_tma_store) {
+                if (it == 0 && store_pending) {            // the box is free once the previous tile's stores have READ it
+                    if (threadIdx.x == 0) tma_store_wait_read();
+                    __syncthreads();
+                }
+                if (active) {
+                    // dense 128-byte rows, 16-byte chunk index XOR (row & 7): CU_TENSOR_MAP_SWIZZLE_128B
+                    RDP_UNROLL
+                    for (int b = 0; b < PL::NB; ++b) {
+                        RDP_UNROLL
+                        for (int r = 0; r < PL::R; ++r) {
+                            const int k = PL::out_index(tid, b, r);
+                            *reinterpret_cast<float2*>(tile_bytes + k * 128 + ((((c >> 1) ^ k) & 7) << 4) + ((c & 1) << 3)) = v[b * PL::R + r];
+                        }
+                    }
+                }
+            } else
+#endif
             if (active) {
                 RDP_UNROLL
                 for (int b = 0; b < PL::NB; ++b) {
@@ -177,6 +205,20 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
                 }
             }
         }
+#ifndef RDP_EMU
+        if (use_tma_store) {
+            tma_store_fence();                             // generic-proxy writes of the box -> visible to the TMA unit
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                constexpr int BR = K1Shape<Plan>::BOX_ROWS;
+                RDP_UNROLL
+                for (int y = 0; y < N; y += BR) tma_store_3d(&tmap_out, tile_bytes + y * 128, 2 * c0, y, mp);
+                tma_store_commit();
+            }
+            store_pending = true;
+            continue;                                      // no store loop, no barrier: on to the next tile's transforms
+        }
+#endif
         __syncthreads();
         // range-major store: row k of the tile -> x_rc[map][k][c0 .. c0+tile_chirps)
         float2* dst = x_rc + map * (long long)N * n_chirps + c0;
@@ -226,6 +268,9 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
         }
         __syncthreads();
     }
+#ifndef RDP_EMU
+    if (store_pending && threadIdx.x == 0) tma_store_wait_read();   // shared memory must outlive the last store's reads
+#endif
 }
 
 #ifndef RDP_EMU

@@ -242,41 +242,6 @@ struct K3Shape {
 };
 
 
-#ifdef RDP_EMU
-struct CUtensorMap_st { alignas(64) unsigned char opaque[128]; };
-typedef CUtensorMap_st CUtensorMap;
-#define RDP_GRID_CONSTANT
-#else
-#include <cuda.h>          // CUtensorMap (type only; nothing from libcuda is linked)
-#define RDP_GRID_CONSTANT __grid_constant__
-// mbarrier + TMA (cp.async.bulk.tensor) primitives, sm_90+ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_%=;\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 3-D tiled TMA load global -> shared; out-of-bounds elements are written as 0 (== cfar_edges ZERO)
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, unsigned long long* bar, int x, int y, int z) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
-}
-// the same box pulled into L2 only (no shared-memory destination): issued a tile ahead of the load that needs it
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int x, int y, int z) {
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(x), "r"(y), "r"(z) : "memory");
-}
-#endif
-
 // pf_c x the sums of the S vertical windows of a strip: wsum[j] = pf_c * sum_{k = j .. j + 2 HL} x[k].  Additions only
 // (a sliding subtraction could cancel a huge line against the rest and fall BELOW the true sum).
 template <int HL, int S>

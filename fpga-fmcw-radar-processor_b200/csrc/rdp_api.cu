@@ -36,7 +36,9 @@ struct K1Launcher {
     size_t (*smem)(int tile_chirps);
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(int grid, size_t smem, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
-                   const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc);
+                   const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc,
+                   int use_tma_store, const CUtensorMap* tmap);
+    int box_rows;                  // range lines per TMA store box
     // thread-block-cluster variant for long chirps (cs = CTAs per cluster; 1 = none)
     int cs;
     size_t smem_cluster;
@@ -90,9 +92,10 @@ struct K1Inst {
         return prepare_kernel(k1_range_kernel<Plan, FMT>, K1Shape<Plan>::THREADS, s, occ);
     }
     static void launch(int grid, size_t s, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
-                       const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc) {
+                       const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc,
+                       int use_tma_store, const CUtensorMap* tmap) {
         RDP_LAUNCH((k1_range_kernel<Plan, FMT>), grid, K1Shape<Plan>::THREADS, s, st, cube, x_rc, win, tw,
-                   n_chirps, tile_chirps, tiles_per_map, total_tiles, sc);
+                   n_chirps, tile_chirps, tiles_per_map, total_tiles, sc, use_tma_store, *tmap);
     }
 #ifndef RDP_EMU
     static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int n_clusters, size_t s, cudaStream_t st) {
@@ -138,12 +141,12 @@ struct K1Inst {
         }
     }
     static K1Launcher get() {
-        return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch,
+        return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch, K1Shape<Plan>::BOX_ROWS,
                           K1Shape<Plan>::CS, K1Shape<Plan>::smem_bytes_cluster(), &prepare_cluster, &launch_cluster};
     }
 #else
     static K1Launcher get() {
-        return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch, 1, 0, nullptr, nullptr};
+        return K1Launcher{Plan::T, K1Shape<Plan>::G, K1Shape<Plan>::TC_MAX, &smem, &prepare, &launch, K1Shape<Plan>::BOX_ROWS, 1, 0, nullptr, nullptr};
     }
 #endif
 };
@@ -325,6 +328,8 @@ struct rdp_handle {
     int k3_variant = 0;             // RDP_K3_VARIANT (tile shape / staging depth of the default CFAR window, A/B measurements)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved at create (NULL: manual tile loads)
     int cfar_tma = 0;               // last CFAR launch staged its tiles with TMA
+    int range_tma = 0;              // last range-stage launch stored its tiles with TMA
+    int knob_k1_tma = -1;           // RDP_K1_TMA: -1 = automatic (int16 input: measured equal or better; complex64: 4 % worse), 0 / 1 = forced
     int k1_tile_chirps = 1;
     size_t k1_smem = 0;
     int k1_max_clusters = 0;       // > 0: the cluster variant of K1 is usable for this shape
@@ -428,7 +433,31 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1
         RDP_CUDA(h, h->k1.launch_cluster(n_clusters, h->k1.smem_cluster, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps,
                                          tiles_per_map, total, sc));
     } else {
-        h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total, sc);
+        CUtensorMap tmap;
+        std::memset(&tmap, 0, sizeof(tmap));
+        int use_tma_store = 0;
+#ifndef RDP_EMU
+        // 16-chirp tiles leave as TMA stores: x_rc seen as [map][range][2 * n_chirps floats], box = 128 bytes x box_rows
+        // lines, 128-byte swizzle (k1_range.cuh).  Peer stores of the sharded mode and narrow tiles keep the store loop.
+        const bool want_tma = h->knob_k1_tma < 0 ? c.input_format == RDP_IN_INT16_IQ : h->knob_k1_tma != 0;
+        if (h->encode_tiled && want_tma && sc.world == 1 && tc == 16 && ((uintptr_t)x_rc & 15) == 0) {
+            typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            const cuuint64_t maps = (cuuint64_t)n_cpi * c.n_channels;
+            const cuuint64_t gdim[3] = {(cuuint64_t)c.n_chirps * 2, (cuuint64_t)c.n_samples, maps};
+            const cuuint64_t gstr[2] = {(cuuint64_t)c.n_chirps * 8, (cuuint64_t)c.n_chirps * c.n_samples * 8};
+            const cuuint32_t box[3] = {32, (cuuint32_t)h->k1.box_rows, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult rr = reinterpret_cast<encode_fn>(h->encode_tiled)(
+                &tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, x_rc, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            use_tma_store = (rr == CUDA_SUCCESS);
+        }
+#endif
+        h->range_tma = use_tma_store;
+        h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total, sc,
+                     use_tma_store, &tmap);
     }
     stage_end(h);
     return launch_check(h, "k1_range_kernel");
@@ -653,6 +682,7 @@ int init_handle(rdp_handle* h) {
         if ((e = std::getenv("RDP_K3_TILES_PER_CTA"))) h->knob_k3_tiles_per_cta = std::atoi(e);
         if ((e = std::getenv("RDP_K12_CTAS"))) h->knob_k12_ctas = std::atoi(e);
         if ((e = std::getenv("RDP_K1_CLUSTER"))) h->knob_k1_cluster = std::atoi(e) != 0;
+        if ((e = std::getenv("RDP_K1_TMA"))) h->knob_k1_tma = std::atoi(e);
         if ((e = std::getenv("RDP_STREAM_PRIORITY"))) h->knob_priority = std::atoi(e);
         if ((e = std::getenv("RDP_K3_DEBUG_SKIP"))) h->knob_k3_debug_skip = std::atoi(e);
         if ((e = std::getenv("RDP_K3_SKEW_NS"))) h->knob_k3_skew_ns = std::atoi(e);

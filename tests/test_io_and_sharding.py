@@ -144,3 +144,37 @@ def test_socket_exchange_three_ranks():
     one = rdp.SocketExchange(rank=0, world=1)
     assert one.all_gather("x") == ["x"]
     one.barrier()
+
+
+def test_track_log_formats_round_trip(tmp_path):
+    """Both track-log formats of the reference (quick: tb_radar_core.vhd:163-181; full with VR= / S=:
+    tb_tactical.vhd:350-363) read back the way model/ADR_visualize.py:124-168 parses them."""
+    trk = np.zeros(3, dtype=rdp.TRACK_DTYPE)
+    trk[0] = (0, 0, 4, 400, -12, 3, 0, 7, 2)
+    trk[1] = (1, 0, 4, 412, -12, 3, 0, 9, 2)
+    trk[2] = (1, 0, 5, 90, 40, -2, 1, 2, 3)
+    active = np.array([[1], [2]], np.int32)
+    for full in (False, True):
+        n = rdp.write_tracks(tmp_path / "t.txt", trk, active, full=full)
+        assert n == 5
+        lines = open(tmp_path / "t.txt").read().split("\n")
+        assert lines[0] == ("TRK 4 R=400 D=-12 VR=3 Q=7 S=10" if full else "TRK 4 R=400 D=-12 Q=7")
+        assert lines[1] == "SCAN_END ACTIVE=1" and lines[4] == "SCAN_END ACTIVE=2"
+        tracks, counts = rdp.read_tracks(tmp_path / "t.txt")
+        assert counts == [1, 2] and tracks[4]["range_q2"] == [400, 412] and tracks[4]["scan"] == [0, 1]
+        assert tracks[5]["quality"] == [2] and tracks[5]["doppler_q2"] == [40]
+
+
+def test_tactical_scenario_generator():
+    """The scenario generator (tb_tactical.vhd:28-40,149-171 analogue): moving targets show up where `truth` says."""
+    sc = rdp.TacticalScenario(n_chirps=32, n_samples=128, targets=((40, 5, 6000.0, 2.0, 0.0), (90, 20, 4000.0, -1.0, 1.0)),
+                              noise_sigma=20.0, clutter_amp=300.0, seed=7)
+    from oracle import float_path as fp
+    for scan in range(3):
+        cube, truth = sc.next_cube()
+        assert cube.shape == (1, 1, 32, 128, 2) and cube.dtype == np.int16
+        m = fp.rd_map(cube[0])[0]
+        for (r, d, a) in truth:
+            r, d = int(round(r)) % 128, int(round(d)) % 32
+            assert m[r, d] > 20 * np.median(m)
+    assert sc.scan == 3 and sc.truth(0)[0][0] == 40 and sc.truth(2)[0][0] == 44
