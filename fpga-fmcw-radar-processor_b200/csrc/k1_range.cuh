@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(K1Shape<Plan>::THREADS)
 k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
                 const float* __restrict__ window, const float2* __restrict__ twtab,
                 int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc,
-                int use_tma_store, const RDP_GRID_CONSTANT CUtensorMap tmap_out) {
+                int use_tma_store, const RDP_GRID_CONSTANT CUtensorMap tmap_out,
+                uint32_t* __restrict__ cpi_flags, int n_channels) {
+    // cpi_flags (nullable, int16 input only): word [map / n_channels] |= RDP_STATUS_ADC_FULL_SCALE when a sample of the
+    // tile sits on a rail -- a running max of |I|, |Q| per thread (two FMNMX per word), one vote per warp and tile
     constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
     constexpr int G = K1Shape<Plan>::G, THREADS = K1Shape<Plan>::THREADS, TCM = K1Shape<Plan>::TC_MAX;
     using P0 = typename Plan::P0;
@@ -166,6 +169,7 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
         const long long map = mp;
         const int c0 = (t - mp * tiles_per_map) * tile_chirps;
         l2_prefetch(t + (int)gridDim.x);
+        float peak = 0.0f;
         for (int it = 0; it < iters; ++it) {
             const int c = it * G + gid;
             const bool active = c < tile_chirps;
@@ -173,6 +177,7 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
             RDP_UNROLL
             for (int i = 0; i < E; ++i) {
                 const float2 s = Raw::cvt(raw[i]);
+                if (IN_FMT == 0) peak = fmaxf(peak, fmaxf(fabsf(s.x), fabsf(s.y)));
                 v[i] = make_float2(s.x * wv[i], s.y * wv[i]);
             }
             if (it + 1 < iters) fetch(t, it + 1);
@@ -204,6 +209,9 @@ k1_range_kernel(const void* __restrict__ cube, float2* __restrict__ x_rc,
                     for (int r = 0; r < PL::R; ++r) tile[PL::out_index(tid, b, r) * tcp + c] = v[b * PL::R + r];
                 }
             }
+        }
+        if (IN_FMT == 0 && cpi_flags != nullptr) {
+            if (__any_sync(0xffffffffu, peak >= 32767.0f) && (threadIdx.x & 31) == 0) atomicOr(cpi_flags + mp / n_channels, 4u);
         }
 #ifndef RDP_EMU
         if (use_tma_store) {

@@ -904,7 +904,8 @@ __device__ __forceinline__ int k4_row_count(const uint32_t* __restrict__ bm, int
 
 __global__ void __launch_bounds__(K4_THREADS)
 k4_row_offsets_kernel(const uint32_t* __restrict__ det_bits, int* __restrict__ row_off, int* __restrict__ counts,
-                      uint32_t* __restrict__ status, CfarArgs a) {
+                      uint32_t* __restrict__ status, CfarArgs a, const uint32_t* __restrict__ cpi_flags) {
+    // cpi_flags (nullable): status bits the earlier stages raised for this CPI (RDP_STATUS_WINDOW_SAT / _ADC_FULL_SCALE)
     // every thread owns `per` consecutive lines; one block-wide exclusive scan of the per-thread totals
     __shared__ int warp_sum[K4_THREADS / 32];
     const int cpi = blockIdx.x;
@@ -959,7 +960,7 @@ k4_row_offsets_kernel(const uint32_t* __restrict__ det_bits, int* __restrict__ r
     }
     if (threadIdx.x == K4_THREADS - 1) {
         counts[cpi] = base;
-        status[cpi] = base > a.max_dets ? (uint32_t)RDP_STATUS_DET_OVERFLOW : 0u;
+        status[cpi] = (base > a.max_dets ? (uint32_t)RDP_STATUS_DET_OVERFLOW : 0u) | (cpi_flags ? cpi_flags[cpi] : 0u);
     }
 }
 

@@ -37,7 +37,7 @@ struct K1Launcher {
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(int grid, size_t smem, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
                    const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc,
-                   int use_tma_store, const CUtensorMap* tmap);
+                   int use_tma_store, const CUtensorMap* tmap, uint32_t* cpi_flags, int n_channels);
     int box_rows;                  // range lines per TMA store box
     // thread-block-cluster variant for long chirps (cs = CTAs per cluster; 1 = none)
     int cs;
@@ -93,9 +93,9 @@ struct K1Inst {
     }
     static void launch(int grid, size_t s, cudaStream_t st, const void* cube, float2* x_rc, const float* win,
                        const float2* tw, int n_chirps, int tile_chirps, int tiles_per_map, long long total_tiles, K1Scatter sc,
-                       int use_tma_store, const CUtensorMap* tmap) {
+                       int use_tma_store, const CUtensorMap* tmap, uint32_t* cpi_flags, int n_channels) {
         RDP_LAUNCH((k1_range_kernel<Plan, FMT>), grid, K1Shape<Plan>::THREADS, s, st, cube, x_rc, win, tw,
-                   n_chirps, tile_chirps, tiles_per_map, total_tiles, sc, use_tma_store, *tmap);
+                   n_chirps, tile_chirps, tiles_per_map, total_tiles, sc, use_tma_store, *tmap, cpi_flags, n_channels);
     }
 #ifndef RDP_EMU
     static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int n_clusters, size_t s, cudaStream_t st) {
@@ -336,9 +336,16 @@ struct rdp_handle {
     CfarArgs cfar;
     TrackState* trk_state = nullptr;   // one track file per channel
     TrackerArgs trk_args;
-    int* rom_dev = nullptr;         // mirrored Q15 Hamming coefficients of the last fixed-point window length
+    int* rom_dev = nullptr;         // mirrored Q15 Hamming coefficients of the last fixed-point window length (tap)
     int rom_n = 0;
     uint32_t* sat_dev = nullptr;
+    uint32_t* cpi_flags[2] = {nullptr, nullptr};   // [chunk] status bits raised before the CFAR stage, by chunk parity
+    // arith = FIXED16: ROMs and Q15 twiddles of both transforms, block exponents of the current chunk
+    int *rom_r = nullptr, *rom_d = nullptr;
+    uint32_t *btw_r = nullptr, *btw_d = nullptr;
+    int *exp_r = nullptr, *exp_d = nullptr;
+    uint32_t* btw_tap = nullptr;    // twiddles of the last rdp_fixed_bfp_fft length
+    int btw_tap_n = 0;
     std::vector<StreamSlot> slots;
     int slot_cpis = 0;
     bool stage_timing = false;
@@ -407,7 +414,8 @@ int launch_check(rdp_handle* h, const char* what) {
 }
 
 // ---- the three stages on device buffers (n_cpi <= any; no chunking here) -------------------
-int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1Scatter* scatter = nullptr) {
+int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1Scatter* scatter = nullptr,
+              uint32_t* cpi_flags = nullptr) {
     const rdp_config& c = h->cfg;
     K1Scatter sc;
     std::memset(&sc, 0, sizeof(sc));
@@ -457,7 +465,7 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1
 #endif
         h->range_tma = use_tma_store;
         h->k1.launch(grid, h->k1_smem, h->cur, cube, x_rc, h->win_r, h->tw_r, c.n_chirps, tc, tiles_per_map, total, sc,
-                     use_tma_store, &tmap);
+                     use_tma_store, &tmap, cpi_flags, c.n_channels);
     }
     stage_end(h);
     return launch_check(h, "k1_range_kernel");
@@ -479,7 +487,7 @@ int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, lon
 // K3 + K4 on n_cpi <= chunk maps-worth of CPIs: bitmask, then ordered compaction into dets / counts / status
 // (all three already offset to this chunk); cpi_label is the CPI index written into the records.
 int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp_det* dets, int* counts,
-             uint32_t* status, int cpi_label, int int_mode = 0, int n_range_rows = 0) {
+             uint32_t* status, int cpi_label, int int_mode = 0, int n_range_rows = 0, const uint32_t* cpi_flags = nullptr) {
     rdp_config c = h->cfg;                                 // by value: n_samples may be overridden (sharded maps)
     CfarArgs args = h->cfar;
     args.int_mode = int_mode;
@@ -489,6 +497,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
         // bitmask / row-offset scratch was sized for the configured map height; grow it if this one is taller
         const size_t need = (size_t)n_cpi * c.n_channels * n_range_rows;
         if (need > h->cfar_rows_cap) {
+            h->scratch_bytes -= (int64_t)(h->cfar_rows_cap * ((size_t)args.words_per_row * sizeof(uint32_t) + sizeof(int)));
             if (h->det_bits) cudaFree(h->det_bits);
             if (h->row_off) cudaFree(h->row_off);
             h->det_bits = nullptr; h->row_off = nullptr;
@@ -549,7 +558,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     int rc = launch_check(h, "k3_cfar_kernel");
     if (rc) return rc;
     stage_begin(h, 3);
-    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, K4_THREADS, 0, h->cur, h->det_bits, h->row_off, counts, status, args);
+    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, K4_THREADS, 0, h->cur, h->det_bits, h->row_off, counts, status, args, cpi_flags);
     const long long total_rows = maps * c.n_samples;
     int lanes_per_row = 1;
     while (lanes_per_row < args.words_per_row && lanes_per_row < 32) lanes_per_row <<= 1;
@@ -582,6 +591,121 @@ k5_pack_dets_kernel(const rdp_det* __restrict__ dets, const int* __restrict__ co
     }
 }
 
+// ---- arith = FIXED16: tables and the three-kernel chain in front of the integer CFAR -------------------------------
+// HAMMING_ROM (window_multiplier.vhd:34-49) read through the mirrored address (:97-102): one coefficient per sample
+std::vector<int> fixed_window_rom(int n) {
+    std::vector<int> coef((size_t)n);
+    const double pi = 3.14159265358979323846;
+    const int rom_size = n / 2;
+    for (int i = 0; i < n; ++i) {
+        int a = i < rom_size ? i : n - 1 - i;
+        if (a > rom_size - 1) a = rom_size - 1;
+        long v = (long)std::floor((0.54 - 0.46 * std::cos(2.0 * pi * (double)a / (double)(n - 1))) * 32767.0 + 0.5);
+        coef[(size_t)i] = (int)(v > 32767 ? 32767 : (v < 0 ? 0 : v));
+    }
+    return coef;
+}
+// Q15 twiddles W_n^k, k < n / 2, as stream words {im[31:16], re[15:0]} (oracle/rtl_fixed.py:bfp_twiddles)
+std::vector<uint32_t> bfp_twiddle_words(int n) {
+    std::vector<uint32_t> w((size_t)(n / 2 > 0 ? n / 2 : 1));
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < n / 2; ++k) {
+        const double ang = 2.0 * pi * (double)k / (double)n;
+        const int re = (int)std::floor(std::cos(ang) * 32767.0 + 0.5), im = (int)std::floor(-std::sin(ang) * 32767.0 + 0.5);
+        w[(size_t)k] = ((uint32_t)(uint16_t)(int16_t)im << 16) | (uint32_t)(uint16_t)(int16_t)re;
+    }
+    return w;
+}
+template <class T>
+int upload_vec(rdp_handle* h, const std::vector<T>& v, T** dev) {
+    int rc = dev_alloc(h, dev, v.size());
+    if (rc) return rc;
+    RDP_CUDA(h, cudaMemcpy(*dev, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    return RDP_OK;
+}
+
+int launch_bfp(rdp_handle* h, const uint32_t* in, uint32_t* out, int* exps, const uint32_t* tw, int n, long long n_frames,
+               const BfpFuse& fu) {
+    if (n_frames == 0) return RDP_OK;
+    int log2n = 0;
+    while ((1 << log2n) < n) ++log2n;
+    const int wpc = 8;                                            // one warp per frame, 8 frames in flight per CTA
+    const size_t smem = (size_t)wpc * n * sizeof(uint32_t);
+#ifndef RDP_EMU
+    if (smem > 48 * 1024) RDP_CUDA(h, cudaFuncSetAttribute(kf_bfp_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+    long long blocks = (n_frames + wpc - 1) / wpc;
+    const long long cap = (long long)h->sm_count * (smem > 64 * 1024 ? 1 : (smem > 32 * 1024 ? 3 : 6));
+    if (blocks > cap) blocks = cap;
+    h->launches += 1;
+    RDP_LAUNCH(kf_bfp_fft_kernel, (unsigned)blocks, 256, smem, h->cur, in, out, exps, tw, n, log2n, n_frames, wpc, fu);
+    return launch_check(h, "kf_bfp_fft_kernel");
+}
+
+int ensure_fixed_tables(rdp_handle* h) {
+    if (h->btw_r) return RDP_OK;
+    const rdp_config& c = h->cfg;
+    int rc = upload_vec(h, fixed_window_rom(c.n_samples), &h->rom_r);
+    if (rc) return rc;
+    rc = upload_vec(h, fixed_window_rom(c.n_chirps), &h->rom_d);
+    if (rc) return rc;
+    rc = upload_vec(h, bfp_twiddle_words(c.n_samples), &h->btw_r);
+    if (rc) return rc;
+    rc = upload_vec(h, bfp_twiddle_words(c.n_chirps), &h->btw_d);
+    if (rc) return rc;
+    rc = dev_alloc(h, &h->exp_r, (size_t)h->chunk * c.n_channels * c.n_chirps);
+    if (rc) return rc;
+    return dev_alloc(h, &h->exp_d, (size_t)h->chunk * c.n_channels * c.n_samples);
+}
+
+// window_multiplier -> range transform -> corner_turner -> doppler_notch -> window_multiplier -> Doppler transform ->
+// magnitude_calc on n_cpi <= chunk CPIs (radar_core.vhd:267-374): three launches, the windows / MTI / magnitude fused
+// into the load and store of the two block-floating-point transforms.  The range-major intermediate (sized for
+// complex64) holds the two 32-bit-word buffers.  mag_map receives the 17-bit magnitude words.
+int run_fixed_front(rdp_handle* h, const void* cube, int n_cpi, uint32_t* mag_map, uint32_t* cpi_flags, int* exp_r_out,
+                    int* exp_d_out) {
+    const rdp_config& c = h->cfg;
+    if (n_cpi == 0) return RDP_OK;
+    int rc = ensure_fixed_tables(h);
+    if (rc) return rc;
+    const long long cells = (long long)cells_per_cpi(c), maps = (long long)n_cpi * c.n_channels;
+    uint32_t* a = reinterpret_cast<uint32_t*>(h->x_rc);
+    uint32_t* b = a + (size_t)h->chunk * cells;
+    BfpFuse fr;
+    fr.adc_check = 1; fr.coef = h->rom_r; fr.sat_flags = cpi_flags; fr.frames_per_flag = (long long)c.n_channels * c.n_chirps;
+    fr.flag_bits = RDP_STATUS_WINDOW_SAT; fr.mti_mode = 0; fr.mag_out = 0;
+    stage_begin(h, 0);
+    rc = launch_bfp(h, reinterpret_cast<const uint32_t*>(cube), a, exp_r_out ? exp_r_out : h->exp_r, h->btw_r, c.n_samples,
+                    maps * c.n_chirps, fr);
+    if (rc) { stage_end(h); return rc; }
+    if (maps > 65535) { stage_end(h); return fail(h, RDP_E_CAPACITY, "fixed-point chain: more than 65535 maps per chunk; lower chunk_cpis"); }
+    h->launches += 1;
+    RDP_LAUNCH(kf_corner_turn_kernel, dim3((c.n_samples + 31) / 32, (c.n_chirps + 31) / 32, (unsigned)maps), 256, 0, h->cur, a, b,
+               c.n_chirps, c.n_samples);
+    stage_end(h);
+    rc = launch_check(h, "kf_corner_turn_kernel");
+    if (rc) return rc;
+    BfpFuse fd;
+    fd.adc_check = 0; fd.coef = h->rom_d; fd.sat_flags = cpi_flags; fd.frames_per_flag = (long long)c.n_channels * c.n_samples;
+    fd.flag_bits = RDP_STATUS_WINDOW_SAT; fd.mti_mode = c.mti_mode; fd.mag_out = 1;
+    stage_begin(h, 1);
+    rc = launch_bfp(h, b, mag_map, exp_d_out ? exp_d_out : h->exp_d, h->btw_d, c.n_chirps, maps * c.n_samples, fd);
+    stage_end(h);
+    return rc;
+}
+
+// Everything in front of the CFAR stage for n_cpi <= chunk CPIs in the handle's arithmetic; `map` receives float32
+// magnitudes (FLOAT32) or 17-bit magnitude words (FIXED16).  flags: this chunk's pre-CFAR status bits (zeroed here).
+int run_front(rdp_handle* h, const void* cube, int n_cpi, float* map, uint32_t* flags, int* exp_r_out = nullptr,
+              int* exp_d_out = nullptr) {
+    if (flags) RDP_CUDA(h, cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)n_cpi, h->cur));
+    if (h->cfg.arith == RDP_ARITH_FIXED16)
+        return run_fixed_front(h, cube, n_cpi, reinterpret_cast<uint32_t*>(map), flags, exp_r_out, exp_d_out);
+    int rc = run_range(h, cube, n_cpi, h->x_rc, nullptr, flags);
+    if (rc) return rc;
+    return run_doppler(h, h->x_rc, n_cpi, map);
+}
+
 int check_cfg(const rdp_config* c) {
     if (!c) return fail(nullptr, RDP_E_INVALID, "config is NULL");
     if (c->struct_size != (int32_t)sizeof(rdp_config))
@@ -610,6 +734,13 @@ int check_cfg(const rdp_config* c) {
         return fail(nullptr, RDP_E_INVALID, "max_dets_per_cpi must be 1..16777216");
     if (c->max_cpis < 1) return fail(nullptr, RDP_E_INVALID, "max_cpis must be >= 1");
     if (c->chunk_cpis < 0) return fail(nullptr, RDP_E_INVALID, "chunk_cpis must be >= 0");
+    if (c->arith != RDP_ARITH_FLOAT32 && c->arith != RDP_ARITH_FIXED16) return fail(nullptr, RDP_E_INVALID, "unknown arith %d", c->arith);
+    if (c->arith == RDP_ARITH_FIXED16) {
+        if (c->input_format != RDP_IN_INT16_IQ || c->mag_mode != RDP_MAG_AMB || c->window_gain != 1.0f)
+            return fail(nullptr, RDP_E_INVALID, "arith FIXED16 needs int16 IQ input, mag_mode AMB and window_gain 1.0");
+        if (c->scale_min > 15 || c->scale_nom > 15 || c->scale_max > 15)
+            return fail(nullptr, RDP_E_INVALID, "arith FIXED16: the RTL's threshold multiplier is 4 bits wide, scales must be 1..15");
+    }
     return RDP_OK;
 }
 
@@ -635,7 +766,8 @@ void release(rdp_handle* h) {
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
-                    h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->rom_dev, h->sat_dev, h->trk_state, h->counts, h->status, h->dets, h->packed, h->l2_flush};
+                    h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->rom_dev, h->sat_dev, h->trk_state, h->counts, h->status, h->dets, h->packed, h->l2_flush,
+                    h->cpi_flags[0], h->cpi_flags[1], h->rom_r, h->rom_d, h->btw_r, h->btw_d, h->exp_r, h->exp_d, h->btw_tap};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -833,6 +965,15 @@ int init_handle(rdp_handle* h) {
     if (rc) return rc;
     rc = dev_alloc(h, &h->status, (size_t)c.max_cpis);
     if (rc) return rc;
+    for (int i = 0; i < 2; ++i) {
+        rc = dev_alloc(h, &h->cpi_flags[i], (size_t)chunk);
+        if (rc) return rc;
+    }
+    if (c.arith == RDP_ARITH_FIXED16) {
+        if (h->k3.trows == 0) return fail(h, RDP_E_INVALID, "arith FIXED16: no tiled integer CFAR instance for this window shape");
+        rc = ensure_fixed_tables(h);
+        if (rc) return rc;
+    }
     return RDP_OK;
 }
 
@@ -887,6 +1028,7 @@ void rdp_default_config(rdp_config* cfg) {
     cfg->max_dets_per_cpi = 4096;
     cfg->max_cpis = 1;
     cfg->chunk_cpis = 0;
+    cfg->arith = RDP_ARITH_FLOAT32;
 }
 
 int rdp_create(const rdp_config* cfg, int32_t device, rdp_handle** out) {
@@ -997,17 +1139,26 @@ int rdp_cfar_stage_u32(rdp_handle* h, const uint32_t* mag_map, int32_t n_cpi, ui
     return RDP_OK;
 }
 
-int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map, rdp_det* dets,
-                       int32_t* n_dets, uint32_t* status) {
-    if (!h || !cube || !dets || !n_dets || !status || n_cpi < 0)
-        return fail(h, RDP_E_INVALID, "rdp_process_device: bad argument");
+// scope guard: the run_* helpers launch on h->cur; whatever path leaves a function, it is the main stream again
+struct CurStreamGuard {
+    rdp_handle* h;
+    explicit CurStreamGuard(rdp_handle* hh) : h(hh) {}
+    ~CurStreamGuard() { h->cur = h->stream; }
+};
+
+static int process_device_impl(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map, int32_t* exp_r, int32_t* exp_d,
+                               rdp_det* dets, int32_t* n_dets, uint32_t* status) {
     const rdp_config& c = h->cfg;
     RDP_CUDA(h, cudaSetDevice(h->device));
     const size_t cells = cells_per_cpi(c);
     const size_t in_stride = cells * in_bytes_per_sample(c);
+    const int int_mode = c.arith == RDP_ARITH_FIXED16;
+    const size_t er_stride = (size_t)c.n_channels * c.n_chirps, ed_stride = (size_t)c.n_channels * c.n_samples;
+    CurStreamGuard guard(h);
     if (h->overlap && !h->stage_timing) {      // per-kernel timing wants the kernels alone on the GPU
         // two-stream chunk pipeline: FFT kernels (HBM-bound) of chunk i+1 on `stream`, CFAR (ALU-bound) of chunk i
-        // on `cfar_stream`; the map scratch is double-buffered, det_bits / row_off belong to the CFAR stream
+        // on `cfar_stream`; the map scratch and the flag words are double-buffered, det_bits / row_off belong to the
+        // CFAR stream
         int k = 0;
         for (int base = 0; base < n_cpi; base += h->chunk, ++k) {
             const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
@@ -1016,15 +1167,14 @@ int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd
             float* map = rd_map ? rd_map + (size_t)base * cells : h->map_scratch[b];
             h->cur = h->stream;
             if (k >= 2) RDP_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_cfar_done[b], 0));
-            int rc = run_range(h, in, n, h->x_rc);
-            if (rc) return rc;
-            rc = run_doppler(h, h->x_rc, n, map);
+            int rc = run_front(h, in, n, map, h->cpi_flags[b], exp_r ? exp_r + (size_t)base * er_stride : nullptr,
+                               exp_d ? exp_d + (size_t)base * ed_stride : nullptr);
             if (rc) return rc;
             RDP_CUDA(h, cudaEventRecord(h->ev_map_ready[b], h->stream));
             h->cur = h->cfar_stream;
             RDP_CUDA(h, cudaStreamWaitEvent(h->cfar_stream, h->ev_map_ready[b], 0));
-            rc = run_cfar(h, map, n, nullptr, dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base);
-            h->cur = h->stream;
+            rc = run_cfar(h, map, n, nullptr, dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base,
+                          int_mode, 0, h->cpi_flags[b]);
             if (rc) return rc;
             RDP_CUDA(h, cudaEventRecord(h->ev_cfar_done[b], h->cfar_stream));
         }
@@ -1035,14 +1185,30 @@ int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd
         const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
         const unsigned char* in = reinterpret_cast<const unsigned char*>(cube) + (size_t)base * in_stride;
         float* map = rd_map ? rd_map + (size_t)base * cells : h->map_scratch[0];
-        int rc = run_range(h, in, n, h->x_rc);
+        int rc = run_front(h, in, n, map, h->cpi_flags[0], exp_r ? exp_r + (size_t)base * er_stride : nullptr,
+                           exp_d ? exp_d + (size_t)base * ed_stride : nullptr);
         if (rc) return rc;
-        rc = run_doppler(h, h->x_rc, n, map);
-        if (rc) return rc;
-        rc = run_cfar(h, map, n, nullptr, dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base);
+        rc = run_cfar(h, map, n, nullptr, dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base, int_mode,
+                      0, h->cpi_flags[0]);
         if (rc) return rc;
     }
     return RDP_OK;
+}
+
+int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map, rdp_det* dets,
+                       int32_t* n_dets, uint32_t* status) {
+    if (!h || !cube || !dets || !n_dets || !status || n_cpi < 0)
+        return fail(h, RDP_E_INVALID, "rdp_process_device: bad argument");
+    return process_device_impl(h, cube, n_cpi, rd_map, nullptr, nullptr, dets, n_dets, status);
+}
+
+int rdp_process_fixed_device(rdp_handle* h, const void* cube, int32_t n_cpi, uint32_t* mag_map, int32_t* exp_range,
+                             int32_t* exp_doppler, rdp_det* dets, int32_t* n_dets, uint32_t* status) {
+    if (!h || !cube || !dets || !n_dets || !status || n_cpi < 0)
+        return fail(h, RDP_E_INVALID, "rdp_process_fixed_device: bad argument");
+    if (h->cfg.arith != RDP_ARITH_FIXED16)
+        return fail(h, RDP_E_INVALID, "rdp_process_fixed_device: the handle was created with arith FLOAT32");
+    return process_device_impl(h, cube, n_cpi, reinterpret_cast<float*>(mag_map), exp_range, exp_doppler, dets, n_dets, status);
 }
 
 int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map, rdp_det* dets,
@@ -1083,12 +1249,10 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
         RDP_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copied[b], 0));
         if (rd_map && k >= 2) RDP_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_mapout[b], 0));
         float* map = h->map_scratch[b];
-        rc = run_range(h, h->in_stage[b], n, h->x_rc);
-        if (rc) return rc;
-        rc = run_doppler(h, h->x_rc, n, map);
+        rc = run_front(h, h->in_stage[b], n, map, h->cpi_flags[b]);
         if (rc) return rc;
         rc = run_cfar(h, map, n, nullptr, h->dets + (size_t)base * c.max_dets_per_cpi, h->counts + base,
-                      h->status + base, base);
+                      h->status + base, base, c.arith == RDP_ARITH_FIXED16, 0, h->cpi_flags[b]);
         if (rc) return rc;
         RDP_CUDA(h, cudaEventRecord(h->ev_done[b], h->stream));
         if (rd_map) {
@@ -1153,20 +1317,10 @@ int rdp_fixed_window(rdp_handle* h, const void* in, int64_t n_rows, int32_t n, v
     if (!h || !in || !out || n_rows < 0 || n < 2 || (n & 1)) return fail(h, RDP_E_INVALID, "rdp_fixed_window: bad argument");
     RDP_CUDA(h, cudaSetDevice(h->device));
     if (h->rom_n != n) {
-        // HAMMING_ROM (window_multiplier.vhd:34-49) and the mirrored address (:97-102), one coefficient per sample
-        std::vector<int> coef(n);
-        const double pi = 3.14159265358979323846;
-        const int rom_size = n / 2;
-        for (int i = 0; i < n; ++i) {
-            int a = i < rom_size ? i : n - 1 - i;
-            if (a > rom_size - 1) a = rom_size - 1;
-            long v = (long)std::floor((0.54 - 0.46 * std::cos(2.0 * pi * (double)a / (double)(n - 1))) * 32767.0 + 0.5);
-            coef[i] = (int)(v > 32767 ? 32767 : (v < 0 ? 0 : v));
-        }
-        if (h->rom_dev) { cudaFree(h->rom_dev); h->rom_dev = nullptr; }
-        int rc = dev_alloc(h, &h->rom_dev, (size_t)n);
+        if (h->rom_dev) { cudaFree(h->rom_dev); h->rom_dev = nullptr; h->scratch_bytes -= (int64_t)sizeof(int) * h->rom_n; }
+        h->rom_n = 0;
+        int rc = upload_vec(h, fixed_window_rom(n), &h->rom_dev);
         if (rc) return rc;
-        RDP_CUDA(h, cudaMemcpy(h->rom_dev, coef.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
         h->rom_n = n;
     }
     if (!h->sat_dev) { int rc = dev_alloc(h, &h->sat_dev, 1); if (rc) return rc; }
@@ -1174,10 +1328,10 @@ int rdp_fixed_window(rdp_handle* h, const void* in, int64_t n_rows, int32_t n, v
     const long long total = (long long)n_rows * n;
     if (total > 0) {
         long long blocks = (total + 255) / 256;
-        if (blocks > 148 * 32) blocks = 148 * 32;
+        if (blocks > h->sm_count * 32) blocks = h->sm_count * 32;
         h->launches += 1;
         RDP_LAUNCH(kf_window_kernel, (unsigned)blocks, 256, 0, h->stream, reinterpret_cast<const uint32_t*>(in),
-                   reinterpret_cast<uint32_t*>(out), h->rom_dev, n, total, h->sat_dev);
+                   reinterpret_cast<uint32_t*>(out), h->rom_dev, n, total, h->sat_dev, total, 1u);
         int rc = launch_check(h, "kf_window_kernel");
         if (rc) return rc;
     }
@@ -1195,7 +1349,7 @@ int rdp_fixed_mti(rdp_handle* h, const void* in, int64_t n_lines, int32_t n, int
     const long long total = (long long)n_lines * n;
     if (total == 0) return RDP_OK;
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > h->sm_count * 32) blocks = h->sm_count * 32;
     h->launches += 1;
     RDP_LAUNCH(kf_mti_kernel, (unsigned)blocks, 256, 0, h->stream, reinterpret_cast<const uint32_t*>(in),
                reinterpret_cast<uint32_t*>(out), n, total, mode);
@@ -1207,7 +1361,7 @@ int rdp_fixed_magnitude(rdp_handle* h, const void* in, int64_t n_words, uint32_t
     RDP_CUDA(h, cudaSetDevice(h->device));
     if (n_words == 0) return RDP_OK;
     long long blocks = (n_words + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > h->sm_count * 32) blocks = h->sm_count * 32;
     h->launches += 1;
     RDP_LAUNCH(kf_magnitude_kernel, (unsigned)blocks, 256, 0, h->stream, reinterpret_cast<const uint32_t*>(in), out,
                (long long)n_words);
@@ -1223,6 +1377,23 @@ int rdp_fixed_corner_turn(rdp_handle* h, const void* in, int32_t n_maps, int32_t
     RDP_LAUNCH(kf_corner_turn_kernel, dim3((n_samples + 31) / 32, (n_chirps + 31) / 32, n_maps), 256, 0, h->stream,
                reinterpret_cast<const uint32_t*>(in), reinterpret_cast<uint32_t*>(out), n_chirps, n_samples);
     return launch_check(h, "kf_corner_turn_kernel");
+}
+
+int rdp_fixed_bfp_fft(rdp_handle* h, const void* in, int64_t n_frames, int32_t n, void* out, int32_t* exps) {
+    if (!h || !in || !out || n_frames < 0 || n < 2 || n > 4096 || !is_pow2(n))
+        return fail(h, RDP_E_INVALID, "rdp_fixed_bfp_fft: bad argument (n must be a power of two in [2, 4096])");
+    RDP_CUDA(h, cudaSetDevice(h->device));
+    if (h->btw_tap_n != n) {
+        if (h->btw_tap) { cudaFree(h->btw_tap); h->btw_tap = nullptr; h->scratch_bytes -= (int64_t)sizeof(uint32_t) * (h->btw_tap_n / 2); }
+        h->btw_tap_n = 0;
+        int rc = upload_vec(h, bfp_twiddle_words(n), &h->btw_tap);
+        if (rc) return rc;
+        h->btw_tap_n = n;
+    }
+    BfpFuse fu;
+    std::memset(&fu, 0, sizeof(fu));
+    return launch_bfp(h, reinterpret_cast<const uint32_t*>(in), reinterpret_cast<uint32_t*>(out), exps, h->btw_tap, n,
+                      (long long)n_frames, fu);
 }
 
 int rdp_tracker_reset(rdp_handle* h, const rdp_tracker_config* cfg) {
@@ -1411,11 +1582,10 @@ int rdp_stream_submit(rdp_handle* h, int32_t slot, const void* cube, int32_t n_c
     RDP_CUDA(h, cudaMemcpyAsync(sl.d_in, cube, in_bytes, cudaMemcpyHostToDevice, sl.copy));
     RDP_CUDA(h, cudaEventRecord(sl.ev_in, sl.copy));
     RDP_CUDA(h, cudaStreamWaitEvent(h->stream, sl.ev_in, 0));
-    int rc = run_range(h, sl.d_in, n_cpi, h->x_rc);
+    int rc = run_front(h, sl.d_in, n_cpi, h->map_scratch[0], h->cpi_flags[0]);
     if (rc) return rc;
-    rc = run_doppler(h, h->x_rc, n_cpi, h->map_scratch[0]);
-    if (rc) return rc;
-    rc = run_cfar(h, h->map_scratch[0], n_cpi, nullptr, sl.d_dets, sl.d_counts, sl.d_status, 0);
+    rc = run_cfar(h, h->map_scratch[0], n_cpi, nullptr, sl.d_dets, sl.d_counts, sl.d_status, 0, c.arith == RDP_ARITH_FIXED16, 0,
+                  h->cpi_flags[0]);
     if (rc) return rc;
     h->launches += 1;
     RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, sl.d_dets, sl.d_counts, sl.d_packed, c.max_dets_per_cpi, 0, 0);

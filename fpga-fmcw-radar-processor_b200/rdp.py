@@ -23,11 +23,14 @@ DEFAULT_LIBRARY = os.path.join(_HERE, "librdp.so")
 RDP_OK = 0
 ERRORS = {-1: "RDP_E_INVALID", -2: "RDP_E_NO_DEVICE", -3: "RDP_E_CUDA", -4: "RDP_E_NOMEM", -5: "RDP_E_CAPACITY"}
 STATUS_DET_OVERFLOW = 1
+STATUS_WINDOW_SAT = 2          # arith="fixed": a window_multiplier output clipped (window_multiplier.vhd:151-158)
+STATUS_ADC_FULL_SCALE = 4      # int16 input: a sample of the CPI sits on a rail
 
 INPUT_FORMATS = {"int16": 0, "complex64": 1}
 MAG_MODES = {"amb": 0, "abs": 1, "pow": 2, "logpow": 3}
 CFAR_AXES = {"as_built": 0, "as_named": 1}
 CFAR_EDGES = {"zero": 0, "raster": 1}
+ARITH = {"float32": 0, "fixed": 1}
 
 # one reported track; layout == struct rdp_track
 TRACK_DTYPE = np.dtype([(n, "<i4") for n in ("cpi", "channel", "id", "range_q2", "doppler_q2", "vel_r", "vel_d",
@@ -49,7 +52,7 @@ class RdpConfig(C.Structure):
         "struct_size", "n_chirps", "n_samples", "n_channels", "cfar_ref_r", "cfar_ref_d", "cfar_guard_r",
         "cfar_guard_d", "rank_pct", "scale_min", "scale_nom", "scale_max", "scale_override", "mti_mode",
         "input_format", "mag_mode", "cfar_axes", "cfar_edges")] + [("window_gain", C.c_float)] + [
-        (n, C.c_int32) for n in ("max_dets_per_cpi", "max_cpis", "chunk_cpis")]
+        (n, C.c_int32) for n in ("max_dets_per_cpi", "max_cpis", "chunk_cpis", "arith")]
 
 
 class RdpTrackerConfig(C.Structure):
@@ -78,6 +81,7 @@ SYMBOLS = {
     "rdp_process_device": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "rdp_process_host": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "rdp_sync": (C.c_int, [_VP]),
+    "rdp_process_fixed_device": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rdp_range_stage": (C.c_int, [_VP, _VP, _I32, _VP]),
     "rdp_doppler_stage": (C.c_int, [_VP, _VP, _I32, _VP]),
     "rdp_cfar_stage": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
@@ -86,6 +90,7 @@ SYMBOLS = {
     "rdp_fixed_mti": (C.c_int, [_VP, _VP, C.c_int64, _I32, _I32, _VP]),
     "rdp_fixed_magnitude": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "rdp_fixed_corner_turn": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP]),
+    "rdp_fixed_bfp_fft": (C.c_int, [_VP, _VP, C.c_int64, _I32, _VP, _VP]),
     "rdp_range_stage_scatter": (C.c_int, [_VP, _VP, _I32, C.POINTER(RdpScatter)]),
     "rdp_doppler_stage_rows": (C.c_int, [_VP, _VP, C.c_int64, _I32, _I32, _VP]),
     "rdp_cfar_stage_rows": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
@@ -191,7 +196,7 @@ class RadarCore:
                  cfar_guard_r=2, cfar_guard_d=1, rank_pct=75, scale_min=2, scale_nom=4, scale_max=6,
                  scale_override=0, mti_mode=0, input_format="int16", mag_mode="amb",
                  cfar_axes="as_built", cfar_edges="zero", window_gain=1.0, max_dets_per_cpi=4096,
-                 max_cpis=1, chunk_cpis=0, device=0, library=None, _test_allow_emulator=False):
+                 max_cpis=1, chunk_cpis=0, arith="float32", device=0, library=None, _test_allow_emulator=False):
         self.lib = load_library(library, _test_allow_emulator)
         cfg = RdpConfig()
         self.lib.rdp_default_config(C.byref(cfg))
@@ -204,6 +209,7 @@ class RadarCore:
             cfg.mag_mode = MAG_MODES[mag_mode]
             cfg.cfar_axes = CFAR_AXES[cfar_axes]
             cfg.cfar_edges = CFAR_EDGES[cfar_edges]
+            cfg.arith = ARITH[arith]
         except KeyError as e:
             raise RdpError(-1, f"unknown option {e}") from None
         cfg.window_gain = window_gain
@@ -216,6 +222,8 @@ class RadarCore:
             raise RdpError(rc, (self.lib.rdp_last_error(None) or b"").decode())
         self.n_range, self.n_doppler, self.n_channels = n_range, n_doppler, n_channels
         self.input_format = input_format
+        self.arith = arith
+        self.map_dtype = np.uint32 if arith == "fixed" else np.float32     # words of the range-Doppler map
         self.max_dets_per_cpi, self.max_cpis = max_dets_per_cpi, max_cpis
         self._pinned = []
         self._out = {}           # page-locked result buffers of process(), reused between calls
@@ -315,7 +323,8 @@ class RadarCore:
 
     def process(self, cube: np.ndarray, want_map: bool = True):
         """HOST buffers in, HOST results out (rdp_process_host).
-        Returns (rd_map float32 [cpi, channel, range, doppler] or None,
+        Returns (rd_map [cpi, channel, range, doppler] or None -- float32, or with arith="fixed" the uint32 17-bit
+                 magnitude words of magnitude_calc,
                  detections DET_DTYPE in canonical (cpi, channel, range, doppler) order,
                  n_dets int32 [cpi] (as found; > max_dets_per_cpi means truncated), status uint32 [cpi]).
         The arrays are views of page-locked buffers owned by this object: valid until the next
@@ -323,7 +332,7 @@ class RadarCore:
         reads freed memory).  process_cpi / process_batch below return copies."""
         cube = self._as_cube(cube)
         n_cpi = cube.shape[0]
-        rd_map = self._out_buffer("map", (n_cpi, self.n_channels, self.n_range, self.n_doppler), np.float32) if want_map else None
+        rd_map = self._out_buffer("map", (n_cpi, self.n_channels, self.n_range, self.n_doppler), self.map_dtype) if want_map else None
         dets = self._out_buffer("dets", (n_cpi * self.max_dets_per_cpi,), DET_DTYPE)
         n_dets = self._out_buffer("n_dets", (n_cpi,), np.int32)
         status = self._out_buffer("status", (n_cpi,), np.uint32)
@@ -337,6 +346,30 @@ class RadarCore:
         """DEVICE buffers in and out, asynchronous (rdp_process_device)."""
         self._check(self.lib.rdp_process_device(self.h, d_cube.ptr, n_cpi, d_map.ptr if d_map else None,
                                                 d_dets.ptr, d_counts.ptr, d_status.ptr))
+
+    def process_fixed(self, cube: np.ndarray):
+        """arith="fixed" with the intermediate words exposed (rdp_process_fixed_device; host arrays in and out).
+        -> (mag uint32 [cpi, channel, range, doppler], exp_range int32 [cpi, channel, chirp],
+            exp_doppler int32 [cpi, channel, range], detections, n_dets, status)."""
+        cube = self._as_cube(cube)
+        n_cpi, n_ch = cube.shape[0], self.n_channels
+        d_in = self.device_buffer(cube.nbytes).upload(cube)
+        d_map = self.device_buffer(n_cpi * self.cells_per_cpi * 4)
+        d_er = self.device_buffer(max(n_cpi * n_ch * self.n_doppler * 4, 16))
+        d_ed = self.device_buffer(max(n_cpi * n_ch * self.n_range * 4, 16))
+        d_dets = self.device_buffer(n_cpi * self.max_dets_per_cpi * DET_DTYPE.itemsize)
+        d_counts, d_status = self.device_buffer(max(n_cpi * 4, 16)), self.device_buffer(max(n_cpi * 4, 16))
+        try:
+            self._check(self.lib.rdp_process_fixed_device(self.h, d_in.ptr, n_cpi, d_map.ptr, d_er.ptr, d_ed.ptr, d_dets.ptr,
+                                                          d_counts.ptr, d_status.ptr))
+            self.sync()
+            dets, counts = self.unpack_device_dets(d_dets, d_counts, n_cpi)
+            return (d_map.download((n_cpi, n_ch, self.n_range, self.n_doppler), np.uint32),
+                    d_er.download((n_cpi, n_ch, self.n_doppler), np.int32), d_ed.download((n_cpi, n_ch, self.n_range), np.int32),
+                    dets, counts, d_status.download((n_cpi,), np.uint32))
+        finally:
+            for b in (d_in, d_map, d_er, d_ed, d_dets, d_counts, d_status):
+                b.free()
 
     def unpack_device_dets(self, d_dets: DeviceBuffer, d_counts: DeviceBuffer, n_cpi: int):
         if n_cpi > self.max_cpis:                                    # the pack scratch holds max_cpis CPIs
@@ -490,6 +523,20 @@ class RadarCore:
             return d_out.download((n_maps, n_samples, n_chirps, 2), np.int16)
         finally:
             d_in.free(); d_out.free()
+
+    def fixed_bfp_fft(self, x: np.ndarray):
+        """The block-floating-point transform of arith="fixed" along the second-to-last axis: x int16 [..., n, 2] ->
+        (X int16 [..., n, 2], exponent int32 [...]), DFT(x) ~= X * 2^exponent (oracle.rtl_fixed.bfp_fft)."""
+        x, d_in, d_out = self._fixed_io(x)
+        n = x.shape[-2]
+        frames = x.size // (2 * n)
+        d_exp = self.device_buffer(max(frames * 4, 16))
+        try:
+            self._check(self.lib.rdp_fixed_bfp_fft(self.h, d_in.ptr, frames, n, d_out.ptr, d_exp.ptr))
+            self.sync()
+            return d_out.download(x.shape, np.int16), d_exp.download(x.shape[:-2], np.int32)
+        finally:
+            d_in.free(); d_out.free(); d_exp.free()
 
     # -- streaming ingest (BASELINE config 5) -------------------------------------------------
     def stream_open(self, n_slots: int = 3, slot_cpis: int = 1):

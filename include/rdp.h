@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RDP_ABI_VERSION 1
+#define RDP_ABI_VERSION 2
 
 enum {
     RDP_OK = 0,
@@ -40,6 +40,17 @@ enum {
 enum { RDP_IN_INT16_IQ = 0, RDP_IN_COMPLEX64 = 1 };
 /* mag_mode: RDP_MAG_AMB is the reference's alpha-max-beta-min (rtl/src/magnitude_calc.vhd:55-81) */
 enum { RDP_MAG_AMB = 0, RDP_MAG_ABS = 1, RDP_MAG_POW = 2, RDP_MAG_LOGPOW = 3 };
+/* RDP_MAG_LOGPOW writes 10 log10(|X|^2) dB (a null cell = -inf is clamped to -300 dB).  The CFAR stage keeps the
+ * reference's MULTIPLICATIVE rule cut > scale * x_k on whatever words the map holds (os_cfar_2d.vhd:200-207 knows
+ * nothing of the map's unit): on a dB map that is a well-defined but unusual statistic, and where the map has
+ * negative words the tile is decided by the exact sign-safe path (slower, identical to the oracle).  A CUT equal to
+ * zero is never a detection (the RTL's output word would be 0 either way).                                        */
+/* arith: FLOAT32 = windows / FFTs / magnitude in float32 (the reference's FFT IP arithmetic is not defined in its
+ * tree); FIXED16 = the 16-bit word-for-word chain of radar_core with the two FFT IP cores replaced by the
+ * self-defined block-floating-point transform of rdp_fixed_bfp_fft ("self-consistent, not Xilinx-exact") and the
+ * integer CFAR of rdp_cfar_stage_u32.  FIXED16 needs int16 input, mag_mode AMB and window_gain 1.0 (the as-built
+ * x2 gain is part of the fixed-point window itself).                                                             */
+enum { RDP_ARITH_FLOAT32 = 0, RDP_ARITH_FIXED16 = 1 };
 /* cfar_axes: AS_BUILT = the RTL's *_RANGE generics act along Doppler and *_DOPPLER along
  * range (rtl/src/os_cfar_2d.vhd:140-146,157-159); AS_NAMED = what the names say.        */
 enum { RDP_AXES_AS_BUILT = 0, RDP_AXES_AS_NAMED = 1 };
@@ -51,8 +62,13 @@ enum { RDP_EDGES_ZERO = 0, RDP_EDGES_RASTER = 1 };
 /* status word bits (one word per CPI) -- the sticky `status_overflow` of
  * rtl/src/radar_core.vhd:447-456 split by cause.                                         */
 enum {
-    RDP_STATUS_DET_OVERFLOW = 1u << 0   /* more than max_dets_per_cpi detections: the list holds the
+    RDP_STATUS_DET_OVERFLOW = 1u << 0,  /* more than max_dets_per_cpi detections: the list holds the
                                            first max_dets_per_cpi in (channel, range, doppler) order */
+    RDP_STATUS_WINDOW_SAT = 1u << 1,    /* FIXED16: a window_multiplier output clipped to 16 bits somewhere in the
+                                           CPI (saturation_flag, rtl/src/window_multiplier.vhd:151-158, which
+                                           radar_core.vhd:447-456 ORs into status_overflow)                  */
+    RDP_STATUS_ADC_FULL_SCALE = 1u << 2 /* int16 input: a sample of the CPI sits on a rail (+32767 / -32768), i.e.
+                                           the ADC (or the synthetic generator) clipped before the path saw it */
 };
 
 /*
@@ -82,8 +98,10 @@ typedef struct rdp_config {
     float   window_gain;       /* 1.0; 2.0 mirrors the as-built x2 of window_multiplier.vhd:146-149 */
     int32_t max_dets_per_cpi;  /* detection-list capacity per CPI                         */
     int32_t max_cpis;          /* largest n_cpi a single rdp_process* call may pass       */
-    int32_t chunk_cpis;        /* CPIs per internal pass (0 = auto: 384 MiB of range-major intermediate,
-                                  the measured optimum on B200)                            */
+    int32_t chunk_cpis;        /* CPIs per internal pass (0 = auto: 1.5 GiB of range-major intermediate for
+                                  device-resident cubes, 384 MiB sub-chunks on the host path: the measured
+                                  optima on B200)                                          */
+    int32_t arith;             /* RDP_ARITH_*                                             */
 } rdp_config;
 
 /* One detection = one `r d mag` record (rtl/src/tb_radar_core.vhd:153-159), with the CPI
@@ -176,11 +194,26 @@ int rdp_process_device(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd
                        rdp_det* dets, int32_t* n_dets, uint32_t* status);
 
 /* Same with HOST buffers (pinned recommended): chunked, host->device and device->host
- * copies overlapped with the kernels on internal streams.  Synchronous.                  */
+ * copies overlapped with the kernels on internal streams.  Synchronous.  n_cpi <= max_cpis.
+ * The detection list comes back PACKED, not in rows: the records of CPI i start at record offset
+ *     sum over k < i of min(n_dets[k], max_dets_per_cpi)
+ * of `dets` (CPI 0 at offset 0; every record carries its cpi index), so `dets` needs room for that sum -- at most
+ * n_cpi * max_dets_per_cpi records -- and only the records found cross PCIe.  rd_map / n_dets / status as above.  */
 int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_map,
                      rdp_det* dets, int32_t* n_dets, uint32_t* status);
 
 int rdp_sync(rdp_handle* h);
+
+/* arith = FIXED16 only: rdp_process_device with the intermediate words exposed (all DEVICE pointers, nullable except
+ * the detection outputs).  mag_map [n_cpi][channel][range][doppler] uint32 = the 17-bit words magnitude_calc hands
+ * to os_cfar_2d; exp_range [n_cpi][channel][chirp] / exp_doppler [n_cpi][channel][range] int32 = the block exponents
+ * of the range / Doppler transform of each frame -- the xfft core's m_axis_data_tuser, which radar_core leaves open
+ * (rtl/src/radar_core.vhd:310,358): the RTL's CFAR therefore compares mantissas of differently scaled range lines,
+ * and so does this mode; a caller that wants calibrated magnitudes multiplies by 2^(exp_range + exp_doppler).
+ * With arith = FIXED16, rdp_process_device / _host / the streaming calls run this chain too; their rd_map then
+ * receives the same uint32 words (cast the pointer), and every record's mag is the word converted to float.     */
+int rdp_process_fixed_device(rdp_handle* h, const void* cube, int32_t n_cpi, uint32_t* mag_map, int32_t* exp_range,
+                             int32_t* exp_doppler, rdp_det* dets, int32_t* n_dets, uint32_t* status);
 
 /* Stage taps on DEVICE buffers -- each RTL stage is separately testable (rtl/src/tb_*.vhd):
  *   range stage   = window_multiplier + range FFT + corner_turner  (radar_core.vhd:267-327)
@@ -196,7 +229,8 @@ int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfa
                    rdp_det* dets, int32_t* n_dets, uint32_t* status);
 
 /* Fixed-point CFAR stage: the map holds UNSIGNED INTEGER magnitudes (the 17-bit words of
- * magnitude_calc; values below 2^24 are supported) and every decision is the bit-exact integer
+ * magnitude_calc; HARD PRECONDITION: every word < 2^24 -- the pre-filter converts words to float and is only
+ * conservative while that is exact; larger words silently lose detections) and every decision is the bit-exact integer
  * arithmetic of rtl/src/os_cfar_2d.vhd:152-217 -- integer sum, mean = floor(sum / N_REF)
  * truncated to 17 bits, lo = mean >> 1, hi = (mean + lo) mod 2^17, exact product x_k * scale.
  * cfar_out (nullable) is the RTL's output word per cell: the CUT magnitude or 0.  Records carry
@@ -221,6 +255,13 @@ int rdp_fixed_mti(rdp_handle* h, const void* in, int64_t n_lines, int32_t n, int
 int rdp_fixed_magnitude(rdp_handle* h, const void* in, int64_t n_words, uint32_t* out);
 int rdp_fixed_corner_turn(rdp_handle* h, const void* in, int32_t n_maps, int32_t n_chirps, int32_t n_samples,
                           void* out);
+/* The transform FIXED16 uses in place of the two Xilinx xfft v9.1 cores (16-bit data and twiddles, block floating
+ * point, convergent rounding: vivado_proj/.../ip/xfft_0_1/xfft_0.xci:12-27,59; their RTL is not in the reference
+ * tree, so this is SELF-DEFINED and stated bit for bit in oracle/rtl_fixed.py:bfp_fft): log2(n) radix-2 DIF stages,
+ * exact integer butterflies with Q15 twiddles and convergent >> 15, one convergent shift per stage for the whole
+ * frame so that it fits 16 bits again; exps[frame] (DEVICE, nullable) = the sum of the shifts, DFT(x) ~= X * 2^exp.
+ * n_frames frames of n words (n = 2..4096, power of two), natural order in and out.                               */
+int rdp_fixed_bfp_fft(rdp_handle* h, const void* in, int64_t n_frames, int32_t n, void* out, int32_t* exps);
 
 /* Streaming ingest (BASELINE config 5: pinned-host, multi-buffered chirp ingest).  n_slots
  * submissions may be in flight; each carries up to slot_cpis CPIs (<= the handle's chunk size).

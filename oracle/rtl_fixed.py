@@ -301,3 +301,130 @@ def detections_from_cfar(cfar_out: np.ndarray) -> np.ndarray:
     range-major order -- the `r d mag` record of rtl/src/tb_radar_core.vhd:153-159."""
     r, d = np.nonzero(cfar_out)
     return np.stack([r, d, np.asarray(cfar_out)[r, d].astype(np.int64)], axis=1).astype(np.int64)
+
+
+# ----------------------------------------------------------------------------
+# Block-floating-point FFT for the end-to-end fixed-point mode
+# ----------------------------------------------------------------------------
+# The reference's two FFTs are Xilinx xfft v9.1 cores: 16-bit data, 16-bit twiddles, block floating point,
+# convergent rounding (vivado_proj/.../ip/xfft_0_1/xfft_0.xci:12-27,59; xfft_doppler_1/xfft_doppler.xci:12-27),
+# whose RTL is NOT in the reference tree and whose block exponent the top level discards
+# (rtl/src/radar_core.vhd:310,358).  Their bit-level arithmetic is therefore unknowable from the tree; the
+# fixed-point mode uses the SELF-DEFINED transform below with the same word widths and rounding rule.
+# It is "self-consistent, not Xilinx-exact" -- PARITY UNPINNED against the FPGA for this stage.
+#
+#   data 16-bit two's complement, twiddles Q15: W_N^k = (round(cos(2 pi k / N) * 32767), round(-sin(..) * 32767))
+#   log2(N) radix-2 decimation-in-frequency stages; in stage s (half = N >> (s+1)), for every pair (a, b) that is
+#   `half` apart inside a block of 2 * half points:
+#       a' = a + b                                    (17 bits)
+#       b' = cround((a - b) * W_N^(pos << s), 15)     complex product in exact integers, convergent >> 15
+#   then ONE shift for the whole frame: sh = the smallest number of bits with ceil(g / 2^sh) <= 32767, g = the
+#   largest |component| of the frame after the butterflies; every component becomes cround(v, sh); exponent += sh.
+#   After the last stage the frame is in bit-reversed order and is written out in natural order.
+#   The transform returns X (int16) and the block exponent e per frame: DFT(x) ~= X * 2^e.
+def bfp_twiddles(n: int):
+    k = np.arange(n // 2, dtype=np.float64)
+    ang = 2.0 * np.pi * k / float(n)
+    wr = np.floor(np.cos(ang) * 32767.0 + 0.5).astype(np.int64)
+    wi = np.floor(-np.sin(ang) * 32767.0 + 0.5).astype(np.int64)
+    return wr, wi
+
+
+def cround(v: np.ndarray, sh) -> np.ndarray:
+    """Convergent (round-half-to-even) arithmetic right shift of integers by `sh` bits (scalar or broadcastable)."""
+    v = np.asarray(v, dtype=np.int64)
+    sh = np.asarray(sh, dtype=np.int64)
+    q = v >> sh
+    rem = v - (q << sh)
+    half = np.where(sh > 0, np.int64(1) << np.maximum(sh - 1, 0), np.int64(0))
+    up = (sh > 0) & ((rem > half) | ((rem == half) & ((q & 1) == 1)))
+    return q + up.astype(np.int64)
+
+
+def _bit_reverse_indices(n: int) -> np.ndarray:
+    m = n.bit_length() - 1
+    idx = np.arange(n)
+    rev = np.zeros(n, dtype=np.int64)
+    for b in range(m):
+        rev |= ((idx >> b) & 1) << (m - 1 - b)
+    return rev
+
+
+def bfp_fft(re: np.ndarray, im: np.ndarray):
+    """Block-floating-point FFT along the LAST axis (length a power of two >= 2) of int16-valued arrays.
+    Returns (re int32 holding int16 values, im likewise, exponent int32 per frame)."""
+    a_re = np.asarray(re).astype(np.int64)
+    a_im = np.asarray(im).astype(np.int64)
+    n = a_re.shape[-1]
+    m = n.bit_length() - 1
+    assert 1 << m == n and n >= 2
+    lead = a_re.shape[:-1]
+    a_re = a_re.reshape(-1, n)
+    a_im = a_im.reshape(-1, n)
+    exp = np.zeros(a_re.shape[0], dtype=np.int64)
+    wr, wi = bfp_twiddles(n)
+    for s in range(m):
+        half = n >> (s + 1)
+        vr = a_re.reshape(-1, 1 << s, 2, half)
+        vi = a_im.reshape(-1, 1 << s, 2, half)
+        tr, br, ti, bi = vr[:, :, 0], vr[:, :, 1], vi[:, :, 0], vi[:, :, 1]
+        sr, si = tr + br, ti + bi
+        dr, di = tr - br, ti - bi
+        idx = np.arange(half) << s
+        cr, ci = wr[idx], wi[idx]
+        pr = cround(dr * cr - di * ci, 15)
+        pi_ = cround(dr * ci + di * cr, 15)
+        g = np.maximum(np.maximum(np.abs(sr), np.abs(si)), np.maximum(np.abs(pr), np.abs(pi_))).reshape(a_re.shape[0], -1).max(axis=1)
+        sh = np.zeros_like(g)
+        for k in range(1, 6):
+            sh = np.where(((g + (1 << sh) - 1) >> sh) > INT16_MAX, k, sh)
+        sh4 = sh[:, None, None]
+        out_r = np.stack([cround(sr, sh4), cround(pr, sh4)], axis=2)
+        out_i = np.stack([cround(si, sh4), cround(pi_, sh4)], axis=2)
+        a_re = out_r.reshape(-1, n)
+        a_im = out_i.reshape(-1, n)
+        exp += sh
+    rev = _bit_reverse_indices(n)
+    x_re = np.empty_like(a_re)
+    x_im = np.empty_like(a_im)
+    x_re[:, rev] = a_re
+    x_im[:, rev] = a_im
+    return (x_re.reshape(lead + (n,)).astype(np.int32), x_im.reshape(lead + (n,)).astype(np.int32),
+            exp.reshape(lead).astype(np.int32))
+
+
+def process_cpi_fixed(frame: np.ndarray, cfar_ref_r=4, cfar_ref_d=4, cfar_guard_r=2, cfar_guard_d=1, rank_pct=75,
+                      scale_min=2, scale_nom=4, scale_max=6, scale_override=0, mti_mode=0, cfar_axes="as_built",
+                      cfar_edges="zero"):
+    """One CPI through the 16-bit chain of radar_core (rtl/src/radar_core.vhd:267-418) word for word:
+    window_multiplier -> range FFT -> corner_turner -> doppler_notch -> window_multiplier -> Doppler FFT ->
+    magnitude_calc -> os_cfar_2d -> non-zero filter, every hand-written stage bit-exact as built (x2 window gain,
+    +1 LSB bias, saturation), the two FFT IP cores replaced by `bfp_fft` above (self-defined: see its header).
+    frame: int16 [channel, chirp, sample, 2] or [chirp, sample, 2].
+    Returns (mag uint32 [channel, range, doppler], detections int64 [n, 4] rows (channel, range, doppler, mag) in
+    canonical order, saturated bool per channel... ORed into one flag, range exponents [channel, chirp],
+    Doppler exponents [channel, range])."""
+    frame = np.asarray(frame)
+    if frame.ndim == 3:
+        frame = frame[None]
+    assert frame.dtype == np.int16 and frame.shape[-1] == 2
+    xi, xq = frame[..., 0].astype(np.int64), frame[..., 1].astype(np.int64)
+    wi, si = window(xi)                                              # range window (radar_core.vhd:267-276)
+    wq, sq = window(xq)
+    saturated = bool(si.any() or sq.any())
+    fr, fi, exp_r = bfp_fft(wi, wq)                                  # range FFT (:303-316)
+    cr, ci = corner_turn(fr), corner_turn(fi)                        # corner turn (:318-327)
+    mr, mi = mti(cr, mti_mode), mti(ci, mti_mode)                    # MTI (:329-338)
+    dwr, s2 = window(mr)                                             # Doppler window (:340-349)
+    dwi, s3 = window(mi)
+    saturated = saturated or bool(s2.any() or s3.any())
+    dr, di, exp_d = bfp_fft(dwr, dwi)                                # Doppler FFT (:351-364)
+    mag = magnitude(dr, di)                                          # magnitude (:366-374)
+    rows = []
+    for ch in range(mag.shape[0]):
+        out = os_cfar_2d(mag[ch], cfar_ref_r, cfar_ref_d, cfar_guard_r, cfar_guard_d, rank_pct, scale_min, scale_nom,
+                         scale_max, scale_override, edges=cfar_edges, axes=cfar_axes)
+        d = detections_from_cfar(out)
+        rows.append(np.concatenate([np.full((len(d), 1), ch, dtype=np.int64), d], axis=1))
+    dets = np.concatenate(rows) if rows else np.zeros((0, 4), np.int64)
+    return mag, dets, saturated, exp_r, exp_d

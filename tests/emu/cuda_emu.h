@@ -184,6 +184,21 @@ static inline int __reduce_add_sync(unsigned m, int v) {
     (void)m;
     return v;
 }
+static inline int __reduce_max_sync(unsigned m, int v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        int nl = std::min(32, emu::ctx()->nthreads - 32 * (emu::tls().lin / 32));
+        int lane = emu::tls().lin % 32;
+        int other = emu::warp_exchange(v, lane ^ o);
+        if ((lane ^ o) < nl) v = std::max(v, other);
+    }
+    (void)m;
+    return v;
+}
+static inline unsigned __brev(unsigned v) {
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+}
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

@@ -22,6 +22,15 @@ def det_cells(d):
     return {(int(x["cpi"]), int(x["channel"]), int(x["range"]), int(x["doppler"])) for x in d}
 
 
+def expected_status(cube):
+    """Status word per CPI of a cube the detection list does not overflow on: RDP_STATUS_ADC_FULL_SCALE (4) for an int16
+    CPI with a sample on a rail, else 0."""
+    cube = np.asarray(cube)
+    if cube.dtype != np.int16:
+        return [0] * cube.shape[0]
+    return [4 if bool((c == 32767).any() or (c == -32768).any()) else 0 for c in cube]
+
+
 def check_canonical(dets):
     key = (dets["cpi"].astype(np.int64) << 48) | (dets["channel"].astype(np.int64) << 40) | \
           (dets["range"].astype(np.int64) << 20) | dets["doppler"].astype(np.int64)
@@ -124,7 +133,7 @@ def case_end_to_end(make_core, n_cpi, n_ch, n_chirps, n_samples, seed=11, fmt="i
     ref_map, ref_dets, ref_counts = fp.process_batch(cube, **okw)
     err = float(np.abs(rd_map - ref_map).max())
     assert err <= MAP_TOL * float(ref_map.max())
-    assert status.tolist() == [0] * n_cpi and launches > 0
+    assert status.tolist() == expected_status(cube) and launches > 0
     check_canonical(dets)
     assert int(n_dets.sum()) == len(dets)
     eps = max(4.0 * err, 1e-7 * float(ref_map.max()))
@@ -233,7 +242,7 @@ def case_end_to_end_mag_modes(make_core, n_ch=2, n_chirps=32, n_samples=64, seed
                 assert err <= 4 * MAP_TOL * float(ref_map.max())
             # the CFAR stage on the GPU's own map is bit-exact against the oracle's CFAR on that same map
             exp = np.concatenate([fp.detections(fp.cfar_stage(rd_map[i, ch]), i, ch) for i in range(2) for ch in range(n_ch)])
-            assert len(exp) == len(dets) and status.tolist() == [0, 0], (fmt, mode)
+            assert len(exp) == len(dets) and status.tolist() == expected_status(cube), (fmt, mode)
             # (a dB map far above 0 dB has no cell 2..6 TIMES its neighbours: the multiplicative rule finds nothing there)
             assert len(dets) > 0 or (mode == "logpow" and scale == 1.0), (fmt, mode)
             for f in ("cpi", "channel", "range", "doppler", "mag"):
@@ -589,3 +598,67 @@ def case_sharded_cpi(make_sharded, make_core, world=4, n_chirps=64, n_samples=12
     assert len(merged) == len(ref_dets) and len(ref_dets) > 0
     for f in ("cpi", "channel", "range", "doppler", "mag"):
         assert np.array_equal(merged[f], ref_dets[f]), f
+
+
+def case_bfp_fft(make_core, sizes=(2, 8, 64, 256, 1024), seed=31):
+    """rdp_fixed_bfp_fft against oracle.rtl_fixed.bfp_fft word for word (mantissas and block exponents): full-scale
+    random frames (every stage shifts), small ones (no stage shifts), an impulse, DC at the rail, all zeros."""
+    rng = np.random.default_rng(seed)
+    with make_core(n_range=64, n_doppler=32) as c:
+        for n in sizes:
+            frames = [rng.integers(-32768, 32768, size=(3, n, 2)), rng.integers(-40, 41, size=(2, n, 2)),
+                      np.zeros((1, n, 2), np.int64), np.full((1, n, 2), 32767), np.full((1, n, 2), -32768)]
+            imp = np.zeros((1, n, 2), np.int64)
+            imp[0, 1 % n, 0] = 32767
+            x = np.concatenate(frames + [imp]).astype(np.int16)
+            y, e = c.fixed_bfp_fft(x)
+            er, ei, ee = fx.bfp_fft(x[..., 0], x[..., 1])
+            assert np.array_equal(y[..., 0], er) and np.array_equal(y[..., 1], ei), n
+            assert np.array_equal(e, ee), n
+            # and it IS a DFT: X * 2^e within the rounding noise of log2(n) 16-bit stages
+            ref = np.fft.fft(x[..., 0].astype(np.float64) + 1j * x[..., 1].astype(np.float64), axis=-1)
+            got = (y[..., 0].astype(np.float64) + 1j * y[..., 1].astype(np.float64)) * (2.0 ** e)[:, None]
+            # rounding noise: <= 1/2 LSB (of the stage's scale) per butterfly, accumulated over the n terms of an output
+            assert np.all(np.abs(got - ref).max(axis=-1) <= (2.0 ** e) * (2.0 * np.sqrt(n) + 4.0)), n
+
+
+def case_fixed_end_to_end(make_core, n_cpi=2, n_ch=2, n_chirps=32, n_samples=64, mti_mode=0, seed=41, amp_scale=1.0, **kw):
+    """arith="fixed": ADC words to detection list through the 16-bit chain, bit-exact against
+    oracle.rtl_fixed.process_cpi_fixed -- magnitude words, both block exponents, the detection list, the status word
+    (window saturation, ADC full scale) -- through rdp_process_fixed_device AND the host path (process)."""
+    cube, _ = st.synthetic_cube(n_cpi, n_ch, n_chirps, n_samples, seed=seed, dtype="int16", n_targets=(2, 4))
+    if amp_scale != 1.0:
+        cube = np.clip(cube.astype(np.float64) * amp_scale, -32768, 32767).astype(np.int16)
+    okw = {k: v for k, v in kw.items() if k not in ("max_dets_per_cpi", "chunk_cpis")}
+    with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, max_cpis=n_cpi, mti_mode=mti_mode, arith="fixed",
+                   max_dets_per_cpi=kw.pop("max_dets_per_cpi", 1 << 14), **kw) as c:
+        mag, er, ed, dets, counts, status = c.process_fixed(cube)
+        m2, dets2, counts2, status2 = (x.copy() for x in c.process(cube))
+    assert m2.dtype == np.uint32 and np.array_equal(m2, mag)
+    assert np.array_equal(dets2, dets) and np.array_equal(counts2, counts) and np.array_equal(status2, status)
+    check_canonical(dets)
+    n_sat = 0
+    for i in range(n_cpi):
+        e_mag, e_dets, e_sat, e_er, e_ed = fx.process_cpi_fixed(cube[i], mti_mode=mti_mode, **okw)
+        assert np.array_equal(mag[i], e_mag), i
+        assert np.array_equal(er[i], e_er) and np.array_equal(ed[i], e_ed), i
+        mine = dets[dets["cpi"] == i]
+        assert len(mine) == len(e_dets) == counts[i], (i, len(mine), len(e_dets))
+        assert np.array_equal(np.stack([mine["channel"], mine["range"], mine["doppler"]], axis=1), e_dets[:, :3])
+        assert np.array_equal(mine["mag"].astype(np.int64), e_dets[:, 3])
+        rail = bool((cube[i] == 32767).any() or (cube[i] == -32768).any())
+        assert int(status[i]) == (2 if e_sat else 0) | (4 if rail else 0), (i, int(status[i]), e_sat, rail)
+        n_sat += int(e_sat)
+    return n_sat
+
+
+def case_adc_full_scale_flag(make_core, n_samples=64, n_chirps=32):
+    """float32 arithmetic, int16 input: RDP_STATUS_ADC_FULL_SCALE is raised for exactly the CPIs that hold a sample on
+    a rail (either rail, I or Q, any channel), and never for complex64 input."""
+    cube, _ = st.synthetic_cube(4, 2, n_chirps, n_samples, seed=5, dtype="int16", n_targets=(1, 2))
+    cube = np.clip(cube, -20000, 20000)
+    cube[1, 0, 3, 7, 0] = 32767
+    cube[2, 1, n_chirps - 1, n_samples - 1, 1] = -32768
+    with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=2, max_cpis=4, max_dets_per_cpi=1 << 14) as c:
+        _, _, _, status = c.process(cube, want_map=False)
+        assert [int(s) & 4 for s in status] == [0, 4, 4, 0]

@@ -36,7 +36,7 @@ def test_struct_layouts():
     lib = rdp.load_library()
     cfg = host.RdpConfig()
     lib.rdp_default_config(C.byref(cfg))
-    assert cfg.struct_size == C.sizeof(host.RdpConfig) == 88
+    assert cfg.struct_size == C.sizeof(host.RdpConfig) == 92
     # reference defaults: rtl/src/radar_core.vhd:12-20, :380
     assert (cfg.n_samples, cfg.n_chirps) == (1024, 128)
     assert (cfg.cfar_ref_r, cfg.cfar_ref_d, cfg.cfar_guard_r, cfg.cfar_guard_d) == (4, 4, 2, 1)
@@ -53,6 +53,11 @@ def test_invalid_config_is_rejected_with_message():
     assert lib.rdp_create(C.byref(cfg), 0, C.byref(h)) == -1
     assert b"n_samples" in lib.rdp_last_error(None)
     cfg.n_samples = 1024
+    cfg.arith = 1                                         # FIXED16 needs int16 input, AMB magnitude, unit window gain
+    cfg.mag_mode = 2
+    assert lib.rdp_create(C.byref(cfg), 0, C.byref(h)) == -1
+    assert b"FIXED16" in lib.rdp_last_error(None)
+    cfg.arith, cfg.mag_mode = 0, 0
     cfg.struct_size = 4
     assert lib.rdp_create(C.byref(cfg), 0, C.byref(h)) == -1
     assert b"ABI" in lib.rdp_last_error(None)

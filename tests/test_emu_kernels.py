@@ -136,3 +136,21 @@ def test_sharded_cpi(make_sharded, make_core, world, kw):
 @pytest.mark.parametrize("seed", range(6))
 def test_cfar_adaptive_stress(make_core, seed):
     pc.case_cfar_adaptive_stress(make_core, seed)
+
+
+def test_bfp_fft(make_core):
+    pc.case_bfp_fft(make_core, sizes=(2, 8, 64, 256))
+
+
+@pytest.mark.parametrize("mti,kw", [(0, dict()), (2, dict(cfar_axes="as_named")), (3, dict(scale_override=3))])
+def test_fixed_end_to_end(make_core, mti, kw):
+    pc.case_fixed_end_to_end(make_core, mti_mode=mti, **kw)
+
+
+def test_fixed_end_to_end_saturating(make_core):
+    # full-scale input: the as-built x2 window gain clips (window_multiplier.vhd:146-158) -> RDP_STATUS_WINDOW_SAT
+    assert pc.case_fixed_end_to_end(make_core, n_cpi=2, n_ch=1, n_chirps=16, n_samples=64, amp_scale=40.0) > 0
+
+
+def test_adc_full_scale_flag(make_core):
+    pc.case_adc_full_scale_flag(make_core)

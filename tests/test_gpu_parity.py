@@ -170,6 +170,36 @@ def test_track_file_from_the_whole_path(make_core, tmp_path):
     assert n == len(trk) + 6 and sum(l.startswith("SCAN_END ACTIVE=") for l in lines) == 6
 
 
+def test_bfp_fft(make_core):
+    """The block-floating-point transform of arith="fixed", every power of two 2 ... 4096, word for word."""
+    pc.case_bfp_fft(make_core, sizes=(2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096))
+
+
+@pytest.mark.parametrize("n_cpi,n_ch,nc,ns,mti,kw", [
+    (2, 1, 128, 1024, 0, dict()),                                   # BASELINE config 2: RTL-native 1024 x 128
+    (2, 12, 256, 512, 0, dict()),                                   # BASELINE config 3: automotive 12 channels
+    (3, 2, 64, 128, 2, dict(cfar_axes="as_named", cfar_edges="raster")),
+    (2, 1, 32, 64, 3, dict(scale_override=3, cfar_ref_r=3, cfar_ref_d=2, cfar_guard_r=1, cfar_guard_d=1)),
+    (1, 1, 8, 4096, 0, dict()), (1, 1, 4096, 8, 2, dict()),
+])
+def test_fixed_end_to_end(make_core, n_cpi, n_ch, nc, ns, mti, kw):
+    """ADC word to detection through the 16-bit chain, bit-exact against the integer oracle."""
+    pc.case_fixed_end_to_end(make_core, n_cpi=n_cpi, n_ch=n_ch, n_chirps=nc, n_samples=ns, mti_mode=mti,
+                             max_dets_per_cpi=1 << 18, **kw)
+
+
+def test_fixed_end_to_end_saturation_and_chunks(make_core):
+    """Full-scale input clips in the as-built x2 window (RDP_STATUS_WINDOW_SAT per CPI); chunked passes and the
+    two-stream overlap keep every CPI's words, exponents and flags in place."""
+    assert pc.case_fixed_end_to_end(make_core, n_cpi=2, n_ch=1, n_chirps=16, n_samples=64, amp_scale=40.0) > 0
+    pc.case_fixed_end_to_end(make_core, n_cpi=7, n_ch=2, n_chirps=32, n_samples=64, chunk_cpis=2, seed=43)
+
+
+def test_adc_full_scale_flag(make_core):
+    pc.case_adc_full_scale_flag(make_core)
+    pc.case_adc_full_scale_flag(make_core, 512, 256)
+
+
 def test_fixed_stages(make_core):
     pc.case_fixed_stages(make_core)
 
