@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--arith", default="float32", choices=["float32", "fixed"],
+                    help="fixed = the 16-bit word-for-word chain (profiling only; use with --no-cpu --no-e2e)")
     ap.add_argument("--shape", default="automotive", choices=sorted(SHAPES), help="profiling only; default = the bench workload")
     args = ap.parse_args()
     global N_CH, N_CHIRPS, N_SAMPLES, CELLS, CFAR_KW, SHAPE_NAME
@@ -213,7 +215,7 @@ def main():
     n_cpi = args.cpis
     core = rdp.RadarCore(n_range=N_SAMPLES, n_doppler=N_CHIRPS, n_channels=N_CH, input_format=args.fmt,
                          max_cpis=max(n_cpi, args.e2e_cpis), chunk_cpis=args.chunk, device=local_rank,
-                         max_dets_per_cpi=args.max_dets, **CFAR_KW)
+                         max_dets_per_cpi=args.max_dets, arith=args.arith, **CFAR_KW)
     info = core.info()
 
     # ---- synthetic batch, resident in HBM before the timed region ----------------------------
@@ -419,8 +421,9 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args.fmt, n_cpi), "cpis_per_gpu_per_step": n_cpi,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.arith == "float32" else "int16 block floating point",
+                "data": "synthetic",
+                "config": {"workload": workload_name(args.fmt, n_cpi) + ("" if args.arith == "float32" else "_fixed16"), "cpis_per_gpu_per_step": n_cpi,
                            "unique_cpis": int(uniq.shape[0]), "chunk_cpis": info["chunk_cpis"],
                            "cfar": ("ref 8/8 guard 4/2" if CFAR_KW else "ref 4/4 guard 2/1") + " rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
                            "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),
