@@ -224,7 +224,7 @@ struct K3Shape {
     static constexpr int ZERO_IDX = SR * SC;
     static constexpr int TF_WORDS = (SR * SC + 4 + 31) / 32 * 32;     // one raw stage (+ a cell that reads 0.0f), 128 B multiple
     // phase 1 runs in rounds of STRIPS_PER_ROUND strips so that their survivors (<= 8 each) always fit the list
-    static constexpr int STRIPS_PER_ROUND = 128, SURV_CAP = S * STRIPS_PER_ROUND;
+    static constexpr int STRIPS_PER_ROUND = THREADS, SURV_CAP = S * STRIPS_PER_ROUND;   // every thread of the CTA takes a strip
     static constexpr int TILE_BYTES = SR * SC * 4;
     static constexpr int N_STRIPS = NBAND * TC;
     static_assert(TR % S == 0 && TR * TC <= 65536 && (SC % 4) == 0 && (PITCH % 8) == 4 && PITCH % 4 == 0, "tile geometry");
@@ -721,6 +721,14 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     const int sub = lane % G, grp = lane / G;
     const bool n_ref_pow2 = (a.n_ref & (a.n_ref - 1)) == 0;
     const double inv_n = 1.0 / (double)a.n_ref;
+    // this lane's NQ window slots as word offsets from the cell (padding slots: the zero cell, addressed absolutely):
+    // fixed for the lane, so they are read once per round instead of once per survivor
+    int soff[NQ];
+    if (warp * (32 / G) < ns) {
+        RDP_UNROLL
+        for (int q = 0; q < NQ; ++q) soff[q] = wtab[2 * (q * G + sub) + 1];
+    }
+    constexpr int NQ_REAL = Sh::NREF / G;                          // slots q < NQ_REAL are reference cells in every lane
     for (int i0 = warp * (32 / G); i0 < ns; i0 += NWARP * (32 / G)) {
         const int i = i0 + grp;
         const bool valid = i < ns;
@@ -731,16 +739,19 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         if (!INT_MODE) {
         const float cut = tf[cidx];
         float v[NQ];
+        const float* tfc = tf + cidx;
         RDP_UNROLL
         for (int q = 0; q < NQ; ++q) {
-            const int2 w = *reinterpret_cast<const int2*>(wtab + 2 * (q * G + sub));
-            v[q] = tf[cidx * w.x + w.y];
+            if (q < NQ_REAL) v[q] = tfc[soff[q]];
+            else v[q] = (q * G + sub < Sh::NREF) ? tfc[soff[q]] : tf[soff[q]];
         }
         float scale = a.s1;
         if (a.adaptive) {
-            double s = 0.0;
+            double s = 0.0, s_b = 0.0;                             // two chains: half the add latency (the sums are exact, the order is free, for any realistic spread of exponents)
             RDP_UNROLL
-            for (int q = 0; q < NQ; ++q) s += (double)v[q];
+            for (int q = 0; q + 1 < NQ; q += 2) { s += (double)v[q]; s_b += (double)v[q + 1]; }
+            if (NQ & 1) s += (double)v[NQ - 1];
+            s += s_b;
             RDP_UNROLL
             for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             // mean = float32(S / N_REF)  (os_cfar_2d.vhd:189); a power-of-two N_REF divides exactly by multiplication
@@ -773,10 +784,11 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         const uint32_t* ti = reinterpret_cast<const uint32_t*>(tf);
         const int cut = (int)ti[cidx];
         int v[NQ];
+        const uint32_t* tic = ti + cidx;
         RDP_UNROLL
         for (int q = 0; q < NQ; ++q) {
-            const int2 w = *reinterpret_cast<const int2*>(wtab + 2 * (q * G + sub));
-            v[q] = (int)ti[cidx * w.x + w.y];
+            if (q < NQ_REAL) v[q] = (int)tic[soff[q]];
+            else v[q] = (int)((q * G + sub < Sh::NREF) ? tic[soff[q]] : ti[soff[q]]);
         }
         int scale = a.is1;
         if (a.adaptive) {
