@@ -177,12 +177,17 @@ def main():
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--arith", default="float32", choices=["float32", "fixed"],
                     help="fixed = the 16-bit word-for-word chain (profiling only; use with --no-cpu --no-e2e)")
+    ap.add_argument("--combine", default="none", choices=["none", "nci"],
+                    help="nci = non-coherent integration over the channels before the CFAR (optional stage; profiling only)")
+    ap.add_argument("--peak-group", action="store_true", help="peak grouping of the detections (optional stage; profiling only)")
     ap.add_argument("--shape", default="automotive", choices=sorted(SHAPES), help="profiling only; default = the bench workload")
     args = ap.parse_args()
     global N_CH, N_CHIRPS, N_SAMPLES, CELLS, CFAR_KW, SHAPE_NAME
     sh = SHAPES[args.shape]
     N_CH, N_CHIRPS, N_SAMPLES, CFAR_KW, SHAPE_NAME = sh["n_ch"], sh["n_chirps"], sh["n_samples"], sh["cfar"], sh["name"]
     CELLS = N_CH * N_CHIRPS * N_SAMPLES
+    if args.combine != "none" or args.peak_group:
+        CFAR_KW = dict(CFAR_KW, combine=args.combine, peak_group=args.peak_group)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -269,7 +274,7 @@ def main():
         t = st_t[name]
         if t["launches"]:
             avg_ms = t["ms"] / t["launches"]
-            cells_per_launch = 2.0 * n_cpi * CELLS / t["launches"]
+            cells_per_launch = 2.0 * n_cpi * (CELLS // N_CH if (name == "cfar" and args.combine == "nci") else CELLS) / t["launches"]
             gbs = cells_per_launch * bpc / (avg_ms * 1e-3) / 1e9
             stages[name] = {"ms_total_per_step": t["ms"] / 2.0, "launches_per_step": t["launches"] // 2,
                             "avg_launch_ms": avg_ms, "alg_bytes_per_cell": bpc, "achieved_gbs": gbs, "frac": gbs / peak}
@@ -423,9 +428,10 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.arith == "float32" else "int16 block floating point",
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.fmt, n_cpi) + ("" if args.arith == "float32" else "_fixed16"), "cpis_per_gpu_per_step": n_cpi,
+                "config": {"workload": workload_name(args.fmt, n_cpi) + ("" if args.arith == "float32" else "_fixed16") +
+                                       ("" if args.combine == "none" else "_nci") + ("_peakgroup" if args.peak_group else ""), "cpis_per_gpu_per_step": n_cpi,
                            "unique_cpis": int(uniq.shape[0]), "chunk_cpis": info["chunk_cpis"],
-                           "cfar": ("ref 8/8 guard 4/2" if CFAR_KW else "ref 4/4 guard 2/1") + " rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
+                           "cfar": ("ref 8/8 guard 4/2" if "cfar_ref_r" in CFAR_KW else "ref 4/4 guard 2/1") + " rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
                            "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),
                            "device": info["device_name"], "cfar_tile_staging": "TMA" if cfar_tma else "manual", "sharding": "CPIs dealt to ranks, no data-path collective",
                            "host_numa_binding": numa},

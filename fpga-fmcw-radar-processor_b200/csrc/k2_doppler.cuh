@@ -6,6 +6,10 @@
 // [range][doppler] (Doppler bin 0 = zero Doppler, natural order).  rows_per_map > 0 leaves pad_rows lines
 // free around every rows_per_map output lines (the CFAR halo of the range-sharded mode).
 //   algorithmic HBM bytes / cell: 8 read + 4 written.
+// COMBINE (optional stage, not in the reference: SURVEY 8f row 3): non-coherent integration over the receive
+// channels -- the FFT group walks the n_combine channels of one (CPI, range line), adds the magnitudes in registers
+// (float32, channel 0 first) and writes ONE line of the combined map [cpi][range][doppler]: 8 read + 4 / n_combine
+// written per input cell, and the CFAR stage then sees one map per CPI instead of n_combine.
 #pragma once
 #include "fft_core.cuh"
 
@@ -33,11 +37,12 @@ __device__ __forceinline__ float magnitude(float2 z) {
     return 10.0f * log10f(fmaxf(p, 1e-30f));
 }
 
-template <class Plan, int MAG>
+template <class Plan, int MAG, bool COMBINE = false>
 __global__ void __launch_bounds__(K2Shape<Plan>::THREADS)
 k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                   const float* __restrict__ window, const float2* __restrict__ twtab,
-                  long long n_rows, int mti_mode, int rows_per_map, int pad_rows) {
+                  long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int n_combine, int n_range) {
+    // COMBINE: n_rows counts OUTPUT lines (cpi, range); input line of channel c = (cpi * n_combine + c) * n_range + range
     constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
     constexpr int G = K2Shape<Plan>::G;
     using P0 = typename Plan::P0;
@@ -59,9 +64,14 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
 
     // software pipeline: the next range line's samples are in flight during the butterflies
     float2 raw[E];
-    auto fetch = [&](long long row) {
+    auto in_row = [&](long long row, int ch) -> long long {
+        if (!COMBINE) return row;
+        const long long cpi = row / n_range;
+        return (cpi * n_combine + ch) * n_range + (row - cpi * n_range);
+    };
+    auto fetch = [&](long long row, int ch) {
         const bool ok = row < n_rows;
-        const float2* src = x_rc + row * N;
+        const float2* src = x_rc + in_row(ok ? row : 0, ch) * N;
         RDP_UNROLL
         for (int b = 0; b < P0::NB; ++b) {
             RDP_UNROLL
@@ -69,17 +79,23 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                 raw[b * P0::R + r] = ok ? __ldg(src + P0::in_index(tid, b, r)) : make_float2(0.f, 0.f);
         }
     };
-    fetch((long long)blockIdx.x * G + gid);
+    fetch((long long)blockIdx.x * G + gid, 0);
 
     for (long long row0 = (long long)blockIdx.x * G; row0 < n_rows; row0 += stride) {
         const long long row = row0 + gid;
         const bool active = row < n_rows;
+        float macc[COMBINE ? E : 1];
+        if (COMBINE) {
+            RDP_UNROLL
+            for (int i = 0; i < (COMBINE ? E : 1); ++i) macc[i] = 0.0f;
+        }
+      for (int ch = 0; ch < (COMBINE ? n_combine : 1); ++ch) {
         float2 v[E];
         if (mti_mode == 0) {
             RDP_UNROLL
             for (int i = 0; i < E; ++i) v[i] = make_float2(raw[i].x * wv[i], raw[i].y * wv[i]);
         } else {                                         // doppler_notch.vhd:72-93, zero initial state (:99-102)
-            const float2* src = x_rc + row * N;
+            const float2* src = x_rc + in_row(active ? row : 0, ch) * N;
             RDP_UNROLL
             for (int b = 0; b < P0::NB; ++b) {
                 RDP_UNROLL
@@ -98,8 +114,14 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                 }
             }
         }
-        fetch(row + stride);
+        if (COMBINE && ch + 1 < n_combine) fetch(row, ch + 1);
+        else fetch(row + stride, 0);
         Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
+        if (COMBINE) {
+            RDP_UNROLL
+            for (int i = 0; i < (COMBINE ? E : 1); ++i) macc[i] += magnitude<MAG>(v[i]);
+            if (ch + 1 < n_combine) continue;
+        }
         if (active) {
             // sharded mode: every map of rows_per_map lines is written with pad_rows halo lines above and below
             const long long orow = rows_per_map > 0 ? row + (2 * (row / rows_per_map) + 1) * pad_rows : row;
@@ -107,9 +129,11 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
             RDP_UNROLL
             for (int b = 0; b < PL::NB; ++b) {
                 RDP_UNROLL
-                for (int r = 0; r < PL::R; ++r) dst[PL::out_index(tid, b, r)] = magnitude<MAG>(v[b * PL::R + r]);
+                for (int r = 0; r < PL::R; ++r)
+                    dst[PL::out_index(tid, b, r)] = COMBINE ? macc[b * PL::R + r] : magnitude<MAG>(v[b * PL::R + r]);
             }
         }
+      }   // channels
     }
 }
 

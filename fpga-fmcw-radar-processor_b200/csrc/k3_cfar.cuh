@@ -891,6 +891,47 @@ k3_cfar_generic_kernel(const float* __restrict__ rd_map, float* __restrict__ cfa
 }
 
 // ------------------------------------------------------------------------------------------
+// K3b (optional, rdp_config.peak_group; not in the reference -- SURVEY 8f row 3 "detection clustering / peak
+// grouping"): a detection survives only if no detection among its 8 neighbours (same map, inside the map) has a
+// larger magnitude -- ties go to the cell that comes first in (range, doppler) raster order -- so a target that
+// spreads over adjacent cells is reported once, at its peak.  One thread per bitmask word; the grouped mask goes to
+// a second buffer (neighbours are read from the ungrouped one).  oracle/float_path.py:peak_group states the rule.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k3b_peak_group_kernel(const uint32_t* __restrict__ bits_in, uint32_t* __restrict__ bits_out, const float* __restrict__ rd_map,
+                      CfarArgs a, long long n_words) {
+    const long long w = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (w >= n_words) return;
+    const long long words_per_map = (long long)a.n_range * a.words_per_row;
+    const long long map = w / words_per_map;
+    const int line = (int)((w - map * words_per_map) / a.words_per_row), word = (int)(w % a.words_per_row);
+    const uint32_t* bm = bits_in + map * words_per_map;
+    const float* m = rd_map + map * (long long)a.n_range * a.n_doppler;
+    const uint32_t in = __ldg(bits_in + w);
+    uint32_t out = in, todo = in;
+    while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const int col = word * 32 + b;
+        const float v = cfar_as_float(__ldg(m + (long long)line * a.n_doppler + col), a.int_mode);
+        bool keep = true;
+        for (int dl = -1; dl <= 1; ++dl) {
+            const int l2 = line + dl;
+            if (l2 < 0 || l2 >= a.n_range) continue;
+            for (int dc = -1; dc <= 1; ++dc) {
+                const int c2 = col + dc;
+                if ((dl == 0 && dc == 0) || c2 < 0 || c2 >= a.n_doppler) continue;
+                if (!((__ldg(bm + (long long)l2 * a.words_per_row + (c2 >> 5)) >> (c2 & 31)) & 1u)) continue;
+                const float v2 = cfar_as_float(__ldg(m + (long long)l2 * a.n_doppler + c2), a.int_mode);
+                if (v2 > v || (v2 == v && (dl < 0 || (dl == 0 && dc < 0)))) keep = false;
+            }
+        }
+        if (!keep) out &= ~(1u << b);
+    }
+    bits_out[w] = out;
+}
+
+// ------------------------------------------------------------------------------------------
 // K4: ordered compaction, two small kernels.  k4_row_offsets: one 1024-thread CTA per CPI counts the set bits
 // of every range line of every channel and exclusive-scans them in (channel, range) order ->
 // per-line record offsets, the CPI's detection count and its status word.  k4_emit: one warp per

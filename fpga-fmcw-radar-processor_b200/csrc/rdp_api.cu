@@ -54,7 +54,7 @@ struct K2Launcher {
     size_t smem;
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(int grid, size_t smem, cudaStream_t st, const float2* x_rc, float* rd_map, const float* win,
-                   const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows);
+                   const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int n_combine, int n_range);
 };
 struct K3Launcher {
     int trows, tcols;            // 0,0 => generic kernel
@@ -154,12 +154,18 @@ struct K1Inst {
 template <class Plan, int MAG>
 struct K2Inst {
     static cudaError_t prepare(size_t s, int* occ) {
-        return prepare_kernel(k2_doppler_kernel<Plan, MAG>, K2Shape<Plan>::THREADS, s, occ);
+        cudaError_t e = prepare_kernel(k2_doppler_kernel<Plan, MAG, true>, K2Shape<Plan>::THREADS, s, nullptr);
+        if (e != cudaSuccess) return e;
+        return prepare_kernel(k2_doppler_kernel<Plan, MAG, false>, K2Shape<Plan>::THREADS, s, occ);
     }
     static void launch(int grid, size_t s, cudaStream_t st, const float2* x_rc, float* rd_map, const float* win,
-                       const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows) {
-        RDP_LAUNCH((k2_doppler_kernel<Plan, MAG>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
-                   n_rows, mti_mode, rows_per_map, pad_rows);
+                       const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int n_combine, int n_range) {
+        if (n_combine > 0)             // non-coherent integration over n_combine channels: n_rows counts OUTPUT lines
+            RDP_LAUNCH((k2_doppler_kernel<Plan, MAG, true>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
+                       n_rows, mti_mode, rows_per_map, pad_rows, n_combine, n_range);
+        else
+            RDP_LAUNCH((k2_doppler_kernel<Plan, MAG, false>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
+                       n_rows, mti_mode, rows_per_map, pad_rows, 1, n_range);
     }
     static K2Launcher get() {
         return K2Launcher{Plan::T, K2Shape<Plan>::G, K2Shape<Plan>::smem_bytes(), &prepare, &launch};
@@ -339,6 +345,9 @@ struct rdp_handle {
     int* rom_dev = nullptr;         // mirrored Q15 Hamming coefficients of the last fixed-point window length (tap)
     int rom_n = 0;
     uint32_t* sat_dev = nullptr;
+    int map_channels = 1;          // maps per CPI the CFAR stage sees: n_channels, or 1 with combine = NCI
+    uint32_t* det_bits2 = nullptr; // peak_group: the grouped bitmask (same shape as det_bits)
+    size_t det_bits2_cap = 0;
     uint32_t* cpi_flags[2] = {nullptr, nullptr};   // [chunk] status bits raised before the CFAR stage, by chunk parity
     // arith = FIXED16: ROMs and Q15 twiddles of both transforms, block exponents of the current chunk
     int *rom_r = nullptr, *rom_d = nullptr;
@@ -379,6 +388,8 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 size_t in_bytes_per_sample(const rdp_config& c) { return c.input_format == RDP_IN_INT16_IQ ? 4 : 8; }
 size_t cells_per_cpi(const rdp_config& c) { return (size_t)c.n_channels * c.n_chirps * c.n_samples; }
+// cells of the range-Doppler map(s) of one CPI: one map per channel, or a single combined map (combine = NCI)
+size_t map_cells_per_cpi(const rdp_config& c) { return (size_t)(c.combine == RDP_COMBINE_NCI ? 1 : c.n_channels) * c.n_chirps * c.n_samples; }
 
 template <class T>
 int dev_alloc(rdp_handle* h, T** p, size_t count) {
@@ -474,12 +485,14 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1
 int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, long long rows_override = -1,
                 int rows_per_map = 0, int pad_rows = 0) {
     const rdp_config& c = h->cfg;
-    const long long rows = rows_override >= 0 ? rows_override : (long long)n_cpi * c.n_channels * c.n_samples;
+    const bool nci = c.combine == RDP_COMBINE_NCI && rows_override < 0;
+    const long long rows = rows_override >= 0 ? rows_override : (long long)n_cpi * (nci ? 1 : c.n_channels) * c.n_samples;
     if (rows == 0) return RDP_OK;
     long long blocks = (rows + h->k2.G - 1) / h->k2.G;
     int grid = (int)(blocks < h->k2_grid_cap ? blocks : h->k2_grid_cap);
     stage_begin(h, 1);
-    h->k2.launch(grid, h->k2.smem, h->cur, x_rc, rd_map, h->win_d, h->tw_d, rows, c.mti_mode, rows_per_map, pad_rows);
+    h->k2.launch(grid, h->k2.smem, h->cur, x_rc, rd_map, h->win_d, h->tw_d, rows, c.mti_mode, rows_per_map, pad_rows,
+                 nci ? c.n_channels : 0, c.n_samples);
     stage_end(h);
     return launch_check(h, "k2_doppler_kernel");
 }
@@ -489,6 +502,7 @@ int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, lon
 int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp_det* dets, int* counts,
              uint32_t* status, int cpi_label, int int_mode = 0, int n_range_rows = 0, const uint32_t* cpi_flags = nullptr) {
     rdp_config c = h->cfg;                                 // by value: n_samples may be overridden (sharded maps)
+    c.n_channels = h->map_channels;                        // maps per CPI (1 after channel combining)
     CfarArgs args = h->cfar;
     args.int_mode = int_mode;
     if (n_range_rows > 0) {
@@ -557,13 +571,27 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     stage_end(h);
     int rc = launch_check(h, "k3_cfar_kernel");
     if (rc) return rc;
+    const uint32_t* bits = h->det_bits;
     stage_begin(h, 3);
-    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, K4_THREADS, 0, h->cur, h->det_bits, h->row_off, counts, status, args, cpi_flags);
+    if (h->cfg.peak_group) {
+        const long long n_words = maps * c.n_samples * args.words_per_row;
+        if (!h->det_bits2 || (size_t)n_words > h->det_bits2_cap) {
+            if (h->det_bits2) { cudaFree(h->det_bits2); h->scratch_bytes -= (int64_t)(h->det_bits2_cap * sizeof(uint32_t)); h->det_bits2 = nullptr; }
+            const size_t cap = (size_t)n_words > h->cfar_rows_cap * (size_t)args.words_per_row ? (size_t)n_words : h->cfar_rows_cap * (size_t)args.words_per_row;
+            int rc2 = dev_alloc(h, &h->det_bits2, cap);
+            if (rc2) { stage_end(h); return rc2; }
+            h->det_bits2_cap = cap;
+        }
+        h->launches += 1;
+        RDP_LAUNCH(k3b_peak_group_kernel, (unsigned)((n_words + 255) / 256), 256, 0, h->cur, h->det_bits, h->det_bits2, rd_map, args, n_words);
+        bits = h->det_bits2;
+    }
+    RDP_LAUNCH(k4_row_offsets_kernel, n_cpi, K4_THREADS, 0, h->cur, bits, h->row_off, counts, status, args, cpi_flags);
     const long long total_rows = maps * c.n_samples;
     int lanes_per_row = 1;
     while (lanes_per_row < args.words_per_row && lanes_per_row < 32) lanes_per_row <<= 1;
     const long long rows_per_cta = 8ll * (32 / lanes_per_row);
-    RDP_LAUNCH(k4_emit_kernel, (unsigned)((total_rows + rows_per_cta - 1) / rows_per_cta), 256, 0, h->cur, h->det_bits,
+    RDP_LAUNCH(k4_emit_kernel, (unsigned)((total_rows + rows_per_cta - 1) / rows_per_cta), 256, 0, h->cur, bits,
                h->row_off, rd_map, dets, args, total_rows, cpi_label, lanes_per_row);
     h->launches += 1;
     stage_end(h);
@@ -735,6 +763,10 @@ int check_cfg(const rdp_config* c) {
     if (c->max_cpis < 1) return fail(nullptr, RDP_E_INVALID, "max_cpis must be >= 1");
     if (c->chunk_cpis < 0) return fail(nullptr, RDP_E_INVALID, "chunk_cpis must be >= 0");
     if (c->arith != RDP_ARITH_FLOAT32 && c->arith != RDP_ARITH_FIXED16) return fail(nullptr, RDP_E_INVALID, "unknown arith %d", c->arith);
+    if (c->combine != RDP_COMBINE_NONE && c->combine != RDP_COMBINE_NCI) return fail(nullptr, RDP_E_INVALID, "unknown combine %d", c->combine);
+    if (c->peak_group != 0 && c->peak_group != 1) return fail(nullptr, RDP_E_INVALID, "peak_group must be 0 or 1");
+    if (c->combine != RDP_COMBINE_NONE && c->arith == RDP_ARITH_FIXED16)
+        return fail(nullptr, RDP_E_INVALID, "channel combining is not part of the RTL chain: use arith FLOAT32");
     if (c->arith == RDP_ARITH_FIXED16) {
         if (c->input_format != RDP_IN_INT16_IQ || c->mag_mode != RDP_MAG_AMB || c->window_gain != 1.0f)
             return fail(nullptr, RDP_E_INVALID, "arith FIXED16 needs int16 IQ input, mag_mode AMB and window_gain 1.0");
@@ -767,7 +799,7 @@ void release(rdp_handle* h) {
     if (h->t1) cudaEventDestroy(h->t1);
     void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
                     h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->rom_dev, h->sat_dev, h->trk_state, h->counts, h->status, h->dets, h->packed, h->l2_flush,
-                    h->cpi_flags[0], h->cpi_flags[1], h->rom_r, h->rom_d, h->btw_r, h->btw_d, h->exp_r, h->exp_d, h->btw_tap};
+                    h->cpi_flags[0], h->cpi_flags[1], h->det_bits2, h->rom_r, h->rom_d, h->btw_r, h->btw_d, h->exp_r, h->exp_d, h->btw_tap};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -869,7 +901,8 @@ int init_handle(rdp_handle* h) {
 
     // CFAR geometry in physical axes (os_cfar_2d.vhd:41-47)
     CfarArgs& a = h->cfar;
-    a.n_range = c.n_samples; a.n_doppler = c.n_chirps; a.n_channels = c.n_channels;
+    h->map_channels = c.combine == RDP_COMBINE_NCI ? 1 : c.n_channels;
+    a.n_range = c.n_samples; a.n_doppler = c.n_chirps; a.n_channels = h->map_channels;
     if (c.cfar_axes == RDP_AXES_AS_BUILT) {
         a.half_l = c.cfar_ref_d + c.cfar_guard_d; a.guard_l = c.cfar_guard_d;
         a.half_c = c.cfar_ref_r + c.cfar_guard_r; a.guard_c = c.cfar_guard_r;
@@ -1029,6 +1062,8 @@ void rdp_default_config(rdp_config* cfg) {
     cfg->max_cpis = 1;
     cfg->chunk_cpis = 0;
     cfg->arith = RDP_ARITH_FLOAT32;
+    cfg->combine = RDP_COMBINE_NONE;
+    cfg->peak_group = 0;
 }
 
 int rdp_create(const rdp_config* cfg, int32_t device, rdp_handle** out) {
@@ -1109,7 +1144,7 @@ int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfa
         return fail(h, RDP_E_INVALID, "rdp_cfar_stage: bad argument");
     const rdp_config& c = h->cfg;
     RDP_CUDA(h, cudaSetDevice(h->device));
-    const size_t cells = cells_per_cpi(c);
+    const size_t cells = map_cells_per_cpi(c);
     for (int base = 0; base < n_cpi; base += h->chunk) {
         const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
         int rc = run_cfar(h, rd_map + (size_t)base * cells, n, cfar_out ? cfar_out + (size_t)base * cells : nullptr,
@@ -1127,7 +1162,7 @@ int rdp_cfar_stage_u32(rdp_handle* h, const uint32_t* mag_map, int32_t n_cpi, ui
         return fail(h, RDP_E_INVALID, "rdp_cfar_stage_u32: no tiled kernel instance for this CFAR window shape");
     const rdp_config& c = h->cfg;
     RDP_CUDA(h, cudaSetDevice(h->device));
-    const size_t cells = cells_per_cpi(c);
+    const size_t cells = map_cells_per_cpi(c);
     for (int base = 0; base < n_cpi; base += h->chunk) {
         const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
         // the kernels move 32-bit words; in integer mode they are read as unsigned integers
@@ -1150,8 +1185,8 @@ static int process_device_impl(rdp_handle* h, const void* cube, int32_t n_cpi, f
                                rdp_det* dets, int32_t* n_dets, uint32_t* status) {
     const rdp_config& c = h->cfg;
     RDP_CUDA(h, cudaSetDevice(h->device));
-    const size_t cells = cells_per_cpi(c);
-    const size_t in_stride = cells * in_bytes_per_sample(c);
+    const size_t cells = map_cells_per_cpi(c);
+    const size_t in_stride = cells_per_cpi(c) * in_bytes_per_sample(c);
     const int int_mode = c.arith == RDP_ARITH_FIXED16;
     const size_t er_stride = (size_t)c.n_channels * c.n_chirps, ed_stride = (size_t)c.n_channels * c.n_samples;
     CurStreamGuard guard(h);
@@ -1221,8 +1256,8 @@ int rdp_process_host(rdp_handle* h, const void* cube, int32_t n_cpi, float* rd_m
     RDP_CUDA(h, cudaSetDevice(h->device));
     int rc = ensure_host_path(h);
     if (rc) return rc;
-    const size_t cells = cells_per_cpi(c);
-    const size_t in_stride = cells * in_bytes_per_sample(c);
+    const size_t cells = map_cells_per_cpi(c);
+    const size_t in_stride = cells_per_cpi(c) * in_bytes_per_sample(c);
     // The detection list goes back chunk by chunk on the D2H stream while later chunks are still being copied in
     // (PCIe is full duplex): after chunk k is queued, the host waits for the counts of chunk k-1 -- long finished,
     // its successor's input copy takes several times its compute -- and queues the copy of its packed records.
@@ -1433,6 +1468,8 @@ int rdp_range_stage_scatter(rdp_handle* h, const void* cube, int32_t n_cpi, cons
     if (!h || !cube || !sc || n_cpi < 0 || sc->world < 1 || sc->world > 16 || sc->rank < 0 || sc->rank >= sc->world)
         return fail(h, RDP_E_INVALID, "rdp_range_stage_scatter: bad argument");
     const rdp_config& c = h->cfg;
+    if (c.combine != RDP_COMBINE_NONE || c.arith != RDP_ARITH_FLOAT32)
+        return fail(h, RDP_E_INVALID, "the sharded-CPI entry points support neither channel combining nor arith FIXED16");
     if (c.n_samples % sc->world != 0 || !is_pow2(c.n_samples / sc->world))
         return fail(h, RDP_E_INVALID, "n_samples / world must be a power of two");
     K1Scatter k;
@@ -1464,6 +1501,7 @@ int rdp_cfar_stage_rows(rdp_handle* h, const float* rd_map, int32_t n_cpi, int32
     if (!h || !rd_map || !dets || !n_dets || !status || n_cpi < 0 || n_range_rows < 1)
         return fail(h, RDP_E_INVALID, "rdp_cfar_stage_rows: bad argument");
     const rdp_config& c = h->cfg;
+    if (c.combine != RDP_COMBINE_NONE) return fail(h, RDP_E_INVALID, "rdp_cfar_stage_rows: not with channel combining");
     RDP_CUDA(h, cudaSetDevice(h->device));
     const size_t cells = (size_t)c.n_channels * n_range_rows * c.n_chirps;
     for (int base = 0; base < n_cpi; base += h->chunk) {

@@ -31,6 +31,7 @@ MAG_MODES = {"amb": 0, "abs": 1, "pow": 2, "logpow": 3}
 CFAR_AXES = {"as_built": 0, "as_named": 1}
 CFAR_EDGES = {"zero": 0, "raster": 1}
 ARITH = {"float32": 0, "fixed": 1}
+COMBINE = {"none": 0, "nci": 1}
 
 # one reported track; layout == struct rdp_track
 TRACK_DTYPE = np.dtype([(n, "<i4") for n in ("cpi", "channel", "id", "range_q2", "doppler_q2", "vel_r", "vel_d",
@@ -52,7 +53,7 @@ class RdpConfig(C.Structure):
         "struct_size", "n_chirps", "n_samples", "n_channels", "cfar_ref_r", "cfar_ref_d", "cfar_guard_r",
         "cfar_guard_d", "rank_pct", "scale_min", "scale_nom", "scale_max", "scale_override", "mti_mode",
         "input_format", "mag_mode", "cfar_axes", "cfar_edges")] + [("window_gain", C.c_float)] + [
-        (n, C.c_int32) for n in ("max_dets_per_cpi", "max_cpis", "chunk_cpis", "arith")]
+        (n, C.c_int32) for n in ("max_dets_per_cpi", "max_cpis", "chunk_cpis", "arith", "combine", "peak_group")]
 
 
 class RdpTrackerConfig(C.Structure):
@@ -196,7 +197,7 @@ class RadarCore:
                  cfar_guard_r=2, cfar_guard_d=1, rank_pct=75, scale_min=2, scale_nom=4, scale_max=6,
                  scale_override=0, mti_mode=0, input_format="int16", mag_mode="amb",
                  cfar_axes="as_built", cfar_edges="zero", window_gain=1.0, max_dets_per_cpi=4096,
-                 max_cpis=1, chunk_cpis=0, arith="float32", device=0, library=None, _test_allow_emulator=False):
+                 max_cpis=1, chunk_cpis=0, arith="float32", combine="none", peak_group=False, device=0, library=None, _test_allow_emulator=False):
         self.lib = load_library(library, _test_allow_emulator)
         cfg = RdpConfig()
         self.lib.rdp_default_config(C.byref(cfg))
@@ -210,10 +211,12 @@ class RadarCore:
             cfg.cfar_axes = CFAR_AXES[cfar_axes]
             cfg.cfar_edges = CFAR_EDGES[cfar_edges]
             cfg.arith = ARITH[arith]
+            cfg.combine = COMBINE[combine]
         except KeyError as e:
             raise RdpError(-1, f"unknown option {e}") from None
         cfg.window_gain = window_gain
         cfg.max_dets_per_cpi, cfg.max_cpis, cfg.chunk_cpis = max_dets_per_cpi, max_cpis, chunk_cpis
+        cfg.peak_group = 1 if peak_group else 0
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.lib.rdp_create(C.byref(cfg), device, C.byref(self.h))
@@ -223,6 +226,7 @@ class RadarCore:
         self.n_range, self.n_doppler, self.n_channels = n_range, n_doppler, n_channels
         self.input_format = input_format
         self.arith = arith
+        self.map_channels = 1 if combine == "nci" else n_channels           # maps per CPI the CFAR stage sees
         self.map_dtype = np.uint32 if arith == "fixed" else np.float32     # words of the range-Doppler map
         self.max_dets_per_cpi, self.max_cpis = max_dets_per_cpi, max_cpis
         self._pinned = []
@@ -332,7 +336,7 @@ class RadarCore:
         reads freed memory).  process_cpi / process_batch below return copies."""
         cube = self._as_cube(cube)
         n_cpi = cube.shape[0]
-        rd_map = self._out_buffer("map", (n_cpi, self.n_channels, self.n_range, self.n_doppler), self.map_dtype) if want_map else None
+        rd_map = self._out_buffer("map", (n_cpi, self.map_channels, self.n_range, self.n_doppler), self.map_dtype) if want_map else None
         dets = self._out_buffer("dets", (n_cpi * self.max_dets_per_cpi,), DET_DTYPE)
         n_dets = self._out_buffer("n_dets", (n_cpi,), np.int32)
         status = self._out_buffer("status", (n_cpi,), np.uint32)
@@ -410,14 +414,14 @@ class RadarCore:
         try:
             self._check(self.lib.rdp_doppler_stage(self.h, d_in.ptr, n_cpi, d_out.ptr))
             self.sync()
-            return d_out.download(x_rc.shape, np.float32)
+            return d_out.download((n_cpi, self.map_channels, self.n_range, self.n_doppler), np.float32)
         finally:
             d_in.free(); d_out.free()
 
     def cfar_stage(self, rd_map: np.ndarray, want_dense: bool = True):
         """-> (detections, n_dets, status, cfar_out or None); cfar_out is the RTL's dense output
         word per cell (CUT magnitude or 0)."""
-        rd_map = np.ascontiguousarray(rd_map, dtype=np.float32).reshape(-1, self.n_channels, self.n_range, self.n_doppler)
+        rd_map = np.ascontiguousarray(rd_map, dtype=np.float32).reshape(-1, self.map_channels, self.n_range, self.n_doppler)
         n_cpi = rd_map.shape[0]
         d_map = self.device_buffer(rd_map.nbytes).upload(rd_map)
         d_dense = self.device_buffer(rd_map.nbytes) if want_dense else None
@@ -566,7 +570,7 @@ class RadarCore:
     def cfar_stage_fixed(self, mag_map: np.ndarray, want_dense: bool = True):
         """Fixed-point CFAR stage (rdp_cfar_stage_u32): unsigned integer magnitudes in, decisions by the
         bit-exact integer arithmetic of rtl/src/os_cfar_2d.vhd.  -> (detections, n_dets, status, cfar_out uint32)."""
-        mag_map = np.ascontiguousarray(mag_map, dtype=np.uint32).reshape(-1, self.n_channels, self.n_range, self.n_doppler)
+        mag_map = np.ascontiguousarray(mag_map, dtype=np.uint32).reshape(-1, self.map_channels, self.n_range, self.n_doppler)
         n_cpi = mag_map.shape[0]
         d_map = self.device_buffer(mag_map.nbytes).upload(mag_map)
         d_dense = self.device_buffer(mag_map.nbytes) if want_dense else None

@@ -51,6 +51,12 @@ enum { RDP_MAG_AMB = 0, RDP_MAG_ABS = 1, RDP_MAG_POW = 2, RDP_MAG_LOGPOW = 3 };
  * integer CFAR of rdp_cfar_stage_u32.  FIXED16 needs int16 input, mag_mode AMB and window_gain 1.0 (the as-built
  * x2 gain is part of the fixed-point window itself).                                                             */
 enum { RDP_ARITH_FLOAT32 = 0, RDP_ARITH_FIXED16 = 1 };
+/* combine (optional stage in front of the CFAR; NOT in the reference, which has one receive channel -- SURVEY.md 8f
+ * row 3): NONE = one range-Doppler map and one CFAR per channel; NCI = non-coherent integration, the magnitudes (in
+ * the configured mag_mode; RDP_MAG_POW gives the classical power integration) of the n_channels channels of a CPI
+ * are added cell by cell (float32, channel 0 first) inside the Doppler stage and the CFAR runs on the ONE combined
+ * map: rd_map is then [n_cpi][1][range][doppler] and every record has channel = 0.  FLOAT32 arithmetic only.     */
+enum { RDP_COMBINE_NONE = 0, RDP_COMBINE_NCI = 1 };
 /* cfar_axes: AS_BUILT = the RTL's *_RANGE generics act along Doppler and *_DOPPLER along
  * range (rtl/src/os_cfar_2d.vhd:140-146,157-159); AS_NAMED = what the names say.        */
 enum { RDP_AXES_AS_BUILT = 0, RDP_AXES_AS_NAMED = 1 };
@@ -102,6 +108,12 @@ typedef struct rdp_config {
                                   device-resident cubes, 384 MiB sub-chunks on the host path: the measured
                                   optima on B200)                                          */
     int32_t arith;             /* RDP_ARITH_*                                             */
+    int32_t combine;           /* RDP_COMBINE_*                                           */
+    int32_t peak_group;        /* 1 = peak grouping of the detections (optional, not in the reference): a detection
+                                  is dropped when one of its 8 neighbouring cells is a detection of larger
+                                  magnitude (ties: the first in (range, doppler) order stays), so a target that
+                                  spreads over adjacent cells is reported once, at its peak.  Counts, overflow
+                                  and the list refer to the grouped detections; cfar_out stays the CFAR output. */
 } rdp_config;
 
 /* One detection = one `r d mag` record (rtl/src/tb_radar_core.vhd:153-159), with the CPI

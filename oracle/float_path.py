@@ -27,6 +27,9 @@ DEFAULTS = dict(
     cfar_axes="as_built",  # as_built | as_named   
     cfar_edges="zero",     # zero | raster          
     window_gain=1.0,       # 1.0, or 2.0 to mirror the as-built x2 gain of the RTL window
+    # optional stages that are NOT in the reference (the RTL has one channel and no grouping):
+    combine="none",        # none | nci: non-coherent integration, magnitudes of all channels added before the CFAR
+    peak_group=False,      # keep a detection only if no neighbouring detection (8-neighbourhood) is larger
 )
 
 
@@ -207,6 +210,28 @@ def detections(cfar_out: np.ndarray, cpi: int = 0, channel: int = 0) -> np.ndarr
     return out
 
 
+def peak_group(cfar_out: np.ndarray) -> np.ndarray:
+    """Peak grouping of one map's CFAR output (CUT or 0 per cell): a detection is dropped when one of its 8
+    neighbours inside the map is a detection of larger magnitude, or of equal magnitude and earlier in (range,
+    doppler) raster order.  Not in the reference; this is the rule librdp's K3b kernel implements."""
+    out = np.asarray(cfar_out)
+    det = out != 0
+    keep = det.copy()
+    nr, nd = out.shape
+    big = np.pad(out.astype(np.float64), 1, constant_values=0.0)
+    dpad = np.pad(det, 1, constant_values=False)
+    for dl in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            if dl == 0 and dc == 0:
+                continue
+            nb = big[1 + dl:1 + dl + nr, 1 + dc:1 + dc + nd]
+            nb_det = dpad[1 + dl:1 + dl + nr, 1 + dc:1 + dc + nd]
+            earlier = dl < 0 or (dl == 0 and dc < 0)
+            beaten = nb_det & ((nb > out) | ((nb == out) & earlier))
+            keep &= ~beaten
+    return np.where(keep, out, np.zeros_like(out))
+
+
 def process_cpi(frame: np.ndarray, **kw):
     """One CPI: frame [chirp, sample(,2)] or [channel, chirp, sample(,2)] ->
     (rd_map float32 [channel, range, doppler], detections DET_DTYPE sorted by
@@ -215,8 +240,15 @@ def process_cpi(frame: np.ndarray, **kw):
     cplx = np.iscomplexobj(frame)
     if frame.ndim == (2 if cplx else 3):
         frame = frame[None]
-    m = rd_map(frame, **kw).astype(np.float32)
-    dets = [detections(cfar_stage(m[c], **kw), 0, c) for c in range(m.shape[0])]
+    p = params(**kw)
+    m = rd_map(frame, **kw)
+    if p["combine"] == "nci":                                   # one combined map per CPI, channel index 0
+        m = m.sum(axis=0, keepdims=True)
+    m = m.astype(np.float32)
+    outs = [cfar_stage(m[c], **kw) for c in range(m.shape[0])]
+    if p["peak_group"]:
+        outs = [peak_group(o) for o in outs]
+    dets = [detections(o, 0, c) for c, o in enumerate(outs)]
     return m, np.concatenate(dets) if dets else np.zeros(0, DET_DTYPE)
 
 

@@ -143,7 +143,7 @@ def case_end_to_end(make_core, n_cpi, n_ch, n_chirps, n_samples, seed=11, fmt="i
         if (i, ch) not in amb_maps:
             amb_maps[(i, ch)] = fp.ambiguous_cells(ref_map[i, ch], eps, **okw)
         assert amb_maps[(i, ch)][r, d], f"detection mismatch at {(i, ch, r, d)} is not near-threshold"
-    assert len(diff) <= max(2, len(ref_dets) // 50)
+    assert len(diff) <= max(2, len(ref_dets) // 500)                    # observed on B200: 0 (bench parity_spot, smoke)
     assert len(ref_dets) > 0
     return len(dets), len(diff)
 
@@ -662,3 +662,44 @@ def case_adc_full_scale_flag(make_core, n_samples=64, n_chirps=32):
     with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=2, max_cpis=4, max_dets_per_cpi=1 << 14) as c:
         _, _, _, status = c.process(cube, want_map=False)
         assert [int(s) & 4 for s in status] == [0, 4, 4, 0]
+
+
+def case_combine_and_group(make_core, n_cpi=2, n_ch=4, n_chirps=32, n_samples=64, fmt="int16", mti_mode=0, seed=51, **kw):
+    """Optional stages in front of / behind the CFAR: non-coherent integration over the channels
+    (one combined map per CPI, fused into the Doppler stage) and peak grouping of the detections.
+    Combined map within MAP_TOL of the oracle's; CFAR (+ grouping) on the GPU's own map bit-exact against the
+    oracle's CFAR (+ grouping) on that same map; end-to-end list identical outside near-threshold cells."""
+    cube, _ = st.synthetic_cube(n_cpi, n_ch, n_chirps, n_samples, seed=seed, dtype=fmt, n_targets=(2, 4))
+    for combine, group in (("nci", False), ("nci", True), ("none", True)):
+        with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, input_format=fmt, max_cpis=n_cpi,
+                       mti_mode=mti_mode, combine=combine, peak_group=group, max_dets_per_cpi=1 << 16, **kw) as c:
+            rd_map, dets, n_dets, status = (x.copy() for x in c.process(cube))
+            tap = c.doppler_stage(c.range_stage(cube))                          # the stage tap combines too
+            d_tap, c_tap, s_tap, dense = c.cfar_stage(rd_map)                    # CFAR stage tap on the combined maps
+        n_maps = 1 if combine == "nci" else n_ch
+        assert rd_map.shape == (n_cpi, n_maps, n_samples, n_chirps) and np.array_equal(tap, rd_map)
+        ref_map, ref_dets, ref_counts = fp.process_batch(cube, mti_mode=mti_mode, combine=combine, peak_group=group, **kw)
+        err = float(np.abs(rd_map - ref_map).max())
+        assert err <= MAP_TOL * float(ref_map.max()), (combine, err)
+        check_canonical(dets)
+        assert int(n_dets.sum()) == len(dets) and status.tolist() == expected_status(cube)
+        # bit-exact on the GPU's own map: CFAR, then grouping
+        exp = []
+        for i in range(n_cpi):
+            for ch in range(n_maps):
+                o = fp.cfar_stage(rd_map[i, ch], **kw)
+                assert np.array_equal(dense[i, ch], o)                          # cfar_out stays the ungrouped CFAR output
+                exp.append(fp.detections(fp.peak_group(o) if group else o, i, ch))
+        exp = np.concatenate(exp)
+        for f in ("cpi", "channel", "range", "doppler", "mag"):
+            assert np.array_equal(dets[f], exp[f]) and np.array_equal(d_tap[f], exp[f]), (combine, group, f)
+        # against the oracle's own map: identical outside near-threshold cells (grouping can move a kept peak only
+        # where the CFAR decision of a neighbour differs, so it is compared on the ungrouped lists' ambiguity)
+        if not group:
+            eps = max(4.0 * err, 1e-7 * float(ref_map.max()))
+            diff = det_cells(dets) ^ det_cells(ref_dets)
+            for (i, ch, r, d) in diff:
+                assert fp.ambiguous_cells(ref_map[i, ch], eps, **kw)[r, d], (combine, (i, ch, r, d))
+        if group:
+            assert len(exp) < sum(int(np.count_nonzero(fp.cfar_stage(rd_map[i, ch], **kw))) for i in range(n_cpi) for ch in range(n_maps))
+        assert len(dets) > 0

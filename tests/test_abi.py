@@ -36,7 +36,7 @@ def test_struct_layouts():
     lib = rdp.load_library()
     cfg = host.RdpConfig()
     lib.rdp_default_config(C.byref(cfg))
-    assert cfg.struct_size == C.sizeof(host.RdpConfig) == 92
+    assert cfg.struct_size == C.sizeof(host.RdpConfig) == 100
     # reference defaults: rtl/src/radar_core.vhd:12-20, :380
     assert (cfg.n_samples, cfg.n_chirps) == (1024, 128)
     assert (cfg.cfar_ref_r, cfg.cfar_ref_d, cfg.cfar_guard_r, cfg.cfar_guard_d) == (4, 4, 2, 1)

@@ -200,6 +200,17 @@ def test_adc_full_scale_flag(make_core):
     pc.case_adc_full_scale_flag(make_core, 512, 256)
 
 
+@pytest.mark.parametrize("n_ch,nc,ns,fmt,mti,kw", [
+    (12, 256, 512, "int16", 0, dict()),                              # BASELINE config 3: 12 channels -> one map
+    (4, 32, 64, "complex64", 2, dict(mag_mode="pow", cfar_edges="raster")),
+    (3, 128, 1024, "int16", 3, dict(cfar_axes="as_named", scale_override=3)),
+    (1, 64, 128, "int16", 0, dict()),                                # one channel: combining is the identity
+])
+def test_combine_and_group(make_core, n_ch, nc, ns, fmt, mti, kw):
+    """non-coherent channel integration fused into the Doppler stage + peak grouping."""
+    pc.case_combine_and_group(make_core, n_ch=n_ch, n_chirps=nc, n_samples=ns, fmt=fmt, mti_mode=mti, **kw)
+
+
 def test_fixed_stages(make_core):
     pc.case_fixed_stages(make_core)
 
