@@ -5,7 +5,11 @@ Every function cites the reference lines it follows (paths relative to
 variable semantics, not what its comments claim.
 
 The FFT IP (Xilinx xfft v9.1) is NOT restated here: its RTL is absent from the
-reference tree, so the fixed-point FFT is "parity unpinned" (oracle/__init__.py).
+reference tree, so the fixed-point FFT is PARITY UNPINNED (oracle/__init__.py).
+`bfp_fft` below is a SELF-DEFINED block-floating-point transform with the IP's
+configured word widths and rounding rule; `process_cpi_fixed` chains it with the
+pinned stages -- the end-to-end fixed-point mode is self-consistent (librdp is
+tested bit for bit against it), not Xilinx-exact.
 """
 from __future__ import annotations
 
