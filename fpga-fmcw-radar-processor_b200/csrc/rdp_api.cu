@@ -1160,6 +1160,8 @@ int rdp_cfar_stage_u32(rdp_handle* h, const uint32_t* mag_map, int32_t n_cpi, ui
         return fail(h, RDP_E_INVALID, "rdp_cfar_stage_u32: bad argument");
     if (h->k3.trows == 0)
         return fail(h, RDP_E_INVALID, "rdp_cfar_stage_u32: no tiled kernel instance for this CFAR window shape");
+    if (h->cfg.scale_min > 15 || h->cfg.scale_nom > 15 || h->cfg.scale_max > 15)
+        return fail(h, RDP_E_INVALID, "rdp_cfar_stage_u32: the RTL's threshold multiplier is 4 bits wide (os_cfar_2d.vhd:204), scales must be 1..15");
     const rdp_config& c = h->cfg;
     RDP_CUDA(h, cudaSetDevice(h->device));
     const size_t cells = map_cells_per_cpi(c);

@@ -284,6 +284,42 @@ def test_device_resident_api_matches_host_api(make_core):
         assert np.array_equal(dets, d_h) and np.array_equal(counts, n_h)
 
 
+def test_c_abi_process_host_packed_layout(make_core):
+    """include/rdp.h: rdp_process_host returns the detection list PACKED -- CPI i at record offset
+    sum(min(n_dets[k], max_dets_per_cpi) for k < i) -- checked through raw ctypes calls (no RadarCore.process), with a
+    list capacity small enough that one CPI overflows (the header used to promise rows)."""
+    import ctypes as C
+    from fpga_fmcw_radar_processor_b200 import rdp as host
+    lib = rdp.load_library()
+    n_cpi, n_ch, nc, ns, cap = 3, 2, 32, 64, 40
+    cube, _ = st.synthetic_cube(n_cpi, n_ch, nc, ns, seed=21, dtype="int16", n_targets=(2, 4))
+    cfg = host.RdpConfig()
+    lib.rdp_default_config(C.byref(cfg))
+    cfg.n_samples, cfg.n_chirps, cfg.n_channels, cfg.max_cpis, cfg.max_dets_per_cpi = ns, nc, n_ch, n_cpi, cap
+    h = C.c_void_p()
+    assert lib.rdp_create(C.byref(cfg), 0, C.byref(h)) == 0, lib.rdp_last_error(None)
+    try:
+        dets = np.zeros(n_cpi * cap, rdp.DET_DTYPE)
+        dets["cpi"] = -1
+        n = np.zeros(n_cpi, np.int32)
+        stat = np.zeros(n_cpi, np.uint32)
+        assert lib.rdp_process_host(h, cube.ctypes.data, n_cpi, None, dets.ctypes.data, n.ctypes.data, stat.ctypes.data) == 0
+    finally:
+        lib.rdp_destroy(h)
+    _, ref_dets, ref_counts = fp.process_batch(cube)
+    assert n.tolist() == ref_counts.tolist() and (n > cap).any() and (n < cap).any()
+    kept = np.minimum(n, cap)
+    off = np.concatenate([[0], np.cumsum(kept)])
+    for i in range(n_cpi):
+        mine = dets[off[i]:off[i + 1]]
+        exp = ref_dets[ref_dets["cpi"] == i][:cap]                 # the first max_dets_per_cpi in canonical order
+        assert np.all(mine["cpi"] == i)
+        for f in ("channel", "range", "doppler"):
+            assert np.array_equal(mine[f], exp[f]), (i, f)
+        assert int(stat[i]) & 1 == int(n[i] > cap)
+    assert np.all(dets["cpi"][off[-1]:] == -1)                     # nothing written past the packed list
+
+
 def test_streaming(make_core):
     pc.case_streaming(make_core)
     pc.case_streaming(make_core, 512, 256, n_sub=5, n_slots=2)
