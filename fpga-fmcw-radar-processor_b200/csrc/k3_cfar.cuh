@@ -537,9 +537,9 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             RDP_UNROLL
             for (int i = 0; i < NP; ++i) { acc[bb][0][i] = 0u; acc[bb][1][i] = 0u; }
         const uint32_t* pl = planes + (S / 2) * b0 + lane * PITCH;
-        RDP_UNROLL
-        for (int k = 0; k <= 2 * HC + 1; ++k) {                    // staged column s0 - HC + k: parity and plane position are compile-time
-            const uint4* src = reinterpret_cast<const uint4*>(pl + ((HC + k) & 1) * PLANE + ((HCP - HC + k) >> 1) * PITCH);
+        // one window column: staged column s0 - HC + k; LEFT / RIGHT = which of the thread's two strips it belongs to
+        auto p0_column = [&](const uint32_t* colp, bool left, bool right) {
+            const uint4* src = reinterpret_cast<const uint4*>(colp);
             uint32_t w[4 * NPL0];
             RDP_UNROLL
             for (int v = 0; v < NPL0; ++v) {
@@ -548,16 +548,32 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             }
             RDP_UNROLL
             for (int bb = 0; bb < P0B; ++bb) {                     // band bb sees the pairs (S / 2) bb .. (S / 2) bb + NP - 1 of this load
-                if (k <= 2 * HC) {
+                if (left) {
                     RDP_UNROLL
                     for (int i = 0; i < NP; ++i) k3_count(acc[bb][0][i], bf16x2_lt_mask(w[(S / 2) * bb + i], td[bb][0]), neg1);
                 }
-                if (k >= 1) {
+                if (right) {
                     RDP_UNROLL
                     for (int i = 0; i < NP; ++i) k3_count(acc[bb][1][i], bf16x2_lt_mask(w[(S / 2) * bb + i], td[bb][1]), neg1);
                 }
             }
+        };
+        // column k sits in plane (HC + k) & 1 at position (HCP - HC + k) >> 1.  The first column belongs to the left strip
+        // only, the last to the right one; the 2 HC columns between them go in HC steps of two (one per plane).
+        // RDP_ROLL_P0 / _P1 keep these loops rolled or unrolled (rdp_common.cuh: measured, unrolled is the default)
+        p0_column(pl + (HC & 1) * PLANE + ((HCP - HC) >> 1) * PITCH, true, false);
+        {
+            const uint32_t* ca = pl + ((HC + 1) & 1) * PLANE + ((HCP - HC + 1) >> 1) * PITCH;     // k = 1, 3, ...
+            const uint32_t* cb = pl + (HC & 1) * PLANE + ((HCP - HC + 2) >> 1) * PITCH;           // k = 2, 4, ...
+            RDP_ROLL_P0
+            for (int kp = 0; kp < HC; ++kp) {
+                p0_column(ca, true, true);
+                p0_column(cb, true, true);
+                ca += PITCH;
+                cb += PITCH;
+            }
         }
+        p0_column(pl + ((HC + 2 * HC + 1) & 1) * PLANE + ((HCP - HC + 2 * HC + 1) >> 1) * PITCH, false, true);
         static_assert(NP0 <= 4 * NPL0, "phase-0 loads");
         RDP_UNROLL
         for (int bb = 0; bb < P0B; ++bb) {
@@ -621,18 +637,23 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             const uint32_t* pa = planes + par0 * PLANE + pos0 * PITCH + (S / 2) * b;
             const uint32_t* pb = planes + (par0 ^ 1) * PLANE + (pos0 + par0) * PITCH + (S / 2) * b;
             uint32_t acc = 0u;
-            RDP_UNROLL
-            for (int kk = 0; kk <= 2 * HC; ++kk) {
-                const uint4* src = reinterpret_cast<const uint4*>((kk & 1) ? pb + (kk / 2) * PITCH : pa + (kk / 2) * PITCH);
+            auto p1s_column = [&](const uint32_t* colp, bool guard_col) {
+                const uint4* src = reinterpret_cast<const uint4*>(colp);
                 uint32_t w[4 * NPL];
                 RDP_UNROLL
                 for (int v = 0; v < NPL; ++v) {
                     const uint4 u = src[v];
                     w[4 * v] = u.x; w[4 * v + 1] = u.y; w[4 * v + 2] = u.z; w[4 * v + 3] = u.w;
                 }
-                const bool guard_col = kk - HC >= -GC && kk - HC <= GC;
                 RDP_UNROLL
                 for (int i = 0; i < NP; ++i) k3_count(acc, bf16x2_lt_mask(w[i], guard_col ? opg[i] : opn[i]), neg1);
+            };
+            // window column kk: plane pa / pb by parity, position kk / 2; rolled, one body per column kind
+            RDP_ROLL_P1
+            for (int kk = 0; kk <= 2 * HC; ++kk) {
+                const uint32_t* colp = ((kk & 1) ? pb : pa) + (kk >> 1) * PITCH;
+                if (kk >= HC - GC && kk <= HC + GC) p1s_column(colp, true);
+                else p1s_column(colp, false);
             }
             const bool keep = ((int)(k3_lo_count(acc) + k3_hi_count(acc)) >= need || cfar_tiny_cut(cut)) &&
                               c0 + tx < a.n_doppler && r0 + S * b + j < a.n_range;
@@ -668,16 +689,14 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
             const int par0 = (s - HC) & 1, pos0 = (s - HC) >> 1;
             const uint32_t* pa = planes + par0 * PLANE + pos0 * PITCH + (S / 2) * b;            // columns s - HC + even
             const uint32_t* pb = planes + (par0 ^ 1) * PLANE + (pos0 + par0) * PITCH + (S / 2) * b;   // columns s - HC + odd
-            RDP_UNROLL
-            for (int kk = 0; kk <= 2 * HC; ++kk) {
-                const uint4* src = reinterpret_cast<const uint4*>((kk & 1) ? pb + (kk / 2) * PITCH : pa + (kk / 2) * PITCH);
+            auto p1d_column = [&](const uint32_t* colp, bool guard_col) {
+                const uint4* src = reinterpret_cast<const uint4*>(colp);
                 uint32_t w[4 * NPL];
                 RDP_UNROLL
                 for (int v = 0; v < NPL; ++v) {
                     const uint4 u = src[v];
                     w[4 * v] = u.x; w[4 * v + 1] = u.y; w[4 * v + 2] = u.z; w[4 * v + 3] = u.w;
                 }
-                const bool guard_col = kk - HC >= -GC && kk - HC <= GC;
                 RDP_UNROLL
                 for (int j = 0; j < S; ++j) {
                     RDP_UNROLL
@@ -691,6 +710,12 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                         else if (in_b) k3_count(acc[j], bf16x2_lt_mask(w[i], th[j]), neg1);
                     }
                 }
+            };
+            RDP_ROLL_P1
+            for (int kk = 0; kk <= 2 * HC; ++kk) {                    // rolled: one body for guard columns, one for the others
+                const uint32_t* colp = ((kk & 1) ? pb : pa) + (kk >> 1) * PITCH;
+                if (kk >= HC - GC && kk <= HC + GC) p1d_column(colp, true);
+                else p1d_column(colp, false);
             }
             uint32_t smask = fmask;
             RDP_UNROLL

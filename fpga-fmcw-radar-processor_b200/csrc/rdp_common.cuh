@@ -14,11 +14,33 @@
 #define RDP_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=] { kernel(__VA_ARGS__); })
 #define RDP_UNROLL
+#define RDP_ROLL_P0
+#define RDP_ROLL_P1
 #else
 #define RDP_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define RDP_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<dim3(grid), dim3(block), (size_t)(smem), (stream)>>>(__VA_ARGS__)
 #define RDP_UNROLL _Pragma("unroll")
+// K3's column loops: rolled (`unroll 1`, -DRDP_K3_ROLL_P0=1 / _P1=1) or fully unrolled (default).  Measured on B200
+// (profiles/r2_summary.md): rolling shrinks the kernel from 5.2 k to 1.8 k SASS instructions but is slower (K3 9.56 ->
+// 10.27 ms with both rolled, 9.56 with phase 0 only): the instruction-fetch stalls it removes cost less than the
+// scheduling freedom and the column-kind branch it adds.
+#ifndef RDP_K3_ROLL_P0
+#define RDP_K3_ROLL_P0 0
+#endif
+#ifndef RDP_K3_ROLL_P1
+#define RDP_K3_ROLL_P1 0
+#endif
+#if RDP_K3_ROLL_P0
+#define RDP_ROLL_P0 _Pragma("unroll 1")
+#else
+#define RDP_ROLL_P0 _Pragma("unroll")
+#endif
+#if RDP_K3_ROLL_P1
+#define RDP_ROLL_P1 _Pragma("unroll 1")
+#else
+#define RDP_ROLL_P1 _Pragma("unroll")
+#endif
 #endif
 
 namespace rdp {
