@@ -1045,17 +1045,20 @@ k4_row_offsets_kernel(const uint32_t* __restrict__ det_bits, int* __restrict__ r
 __global__ void __launch_bounds__(256)
 k4_emit_kernel(const uint32_t* __restrict__ det_bits, const int* __restrict__ row_off, const float* __restrict__ rd_map,
                rdp_det* __restrict__ dets, CfarArgs a, long long total_rows, int cpi_label_base, int lanes_per_row) {
-    // lanes_per_row = power of two >= min(words_per_row, 32): a warp serves 32 / lanes_per_row range lines at once
+    // lanes_per_row = power of two >= min(words_per_row, 32): a warp serves 32 / lanes_per_row range lines at once.
+    // total_rows < 2^31 (the host caps a chunk): 32-bit index arithmetic, the record's CPI / channel / range once per line
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int rows_per_warp = 32 / lanes_per_row;
     const int sub = lane % lanes_per_row;
-    const long long row = ((long long)blockIdx.x * 8 + warp) * rows_per_warp + lane / lanes_per_row;
-    const bool row_ok = row < total_rows;
-    const int rows_per_cpi = a.n_channels * a.n_range;
-    const int cpi = row_ok ? (int)(row / rows_per_cpi) : 0, line_all = row_ok ? (int)(row % rows_per_cpi) : 0;
-    const uint32_t* bm = det_bits + (row_ok ? row : 0) * a.words_per_row;
+    const unsigned row = ((unsigned)blockIdx.x * 8u + (unsigned)warp) * (unsigned)rows_per_warp + (unsigned)(lane / lanes_per_row);
+    const bool row_ok = row < (unsigned)total_rows;
+    const unsigned rows_per_cpi = (unsigned)(a.n_channels * a.n_range);
+    const unsigned cpi = row_ok ? row / rows_per_cpi : 0u, line_all = row_ok ? row - cpi * rows_per_cpi : 0u;
+    const int channel = (int)(line_all / (unsigned)a.n_range), range = (int)(line_all - (unsigned)channel * (unsigned)a.n_range);
+    const uint32_t* bm = det_bits + (size_t)(row_ok ? row : 0u) * a.words_per_row;
+    const float* mrow = rd_map + (size_t)(row_ok ? row : 0u) * a.n_doppler;
     int base = row_ok ? __ldg(row_off + row) : 0;
-    rdp_det* out = dets + (long long)cpi * a.max_dets;
+    rdp_det* out = dets + (size_t)cpi * a.max_dets;
     for (int w0 = 0; w0 < a.words_per_row; w0 += lanes_per_row) {
         const int w = w0 + sub;
         uint32_t word = (row_ok && w < a.words_per_row) ? __ldg(bm + w) : 0u;
@@ -1073,11 +1076,11 @@ k4_emit_kernel(const uint32_t* __restrict__ det_bits, const int* __restrict__ ro
             if (slot < a.max_dets) {
                 const int col = w * 32 + b;
                 rdp_det d;
-                d.cpi = cpi_label_base + cpi;
-                d.channel = line_all / a.n_range;
-                d.range = line_all % a.n_range;
+                d.cpi = cpi_label_base + (int)cpi;
+                d.channel = channel;
+                d.range = range;
                 d.doppler = col;
-                d.mag = cfar_as_float(__ldg(rd_map + row * a.n_doppler + col), a.int_mode);
+                d.mag = cfar_as_float(__ldg(mrow + col), a.int_mode);
                 out[slot] = d;
             }
             ++slot;

@@ -524,6 +524,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     }
     const long long maps = (long long)n_cpi * c.n_channels;
     if (maps == 0) return RDP_OK;
+    if (maps * c.n_samples >= (1ll << 31)) return fail(h, RDP_E_CAPACITY, "CFAR stage: too many range lines in one launch; lower chunk_cpis");
     if (h->k3.trows != 0) {
         const long long tiles = maps * ((c.n_samples + h->k3.trows - 1) / h->k3.trows) * ((c.n_chirps + h->k3.tcols - 1) / h->k3.tcols);
         if (tiles >= (1ll << 31)) return fail(h, RDP_E_CAPACITY, "CFAR stage: too many tiles in one launch; lower chunk_cpis");
