@@ -298,7 +298,9 @@ template <int HL, int HC, int GL, int GC, int TR, int NSTAGE, int P0B, bool INT_
 __global__ void __launch_bounds__((K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>::THREADS), (K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>::occupancy_hint()))
 k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, uint32_t* __restrict__ det_bits,
                CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
-               const RDP_GRID_CONSTANT CUtensorMap tmap) {
+               const RDP_GRID_CONSTANT CUtensorMap tmap, uint32_t* __restrict__ cpi_flags) {
+    // cpi_flags (nullable, INT_MODE): word [map / n_channels] |= RDP_STATUS_MAP_RANGE when a tile holds a magnitude word
+    // >= 2^24 (the packed pre-filter converts words to float and is only conservative while that is exact)
     using Sh = K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>;
     constexpr int S = Sh::S, TC = Sh::TC, SC = Sh::SC, SR = Sh::SR, SRP = Sh::SRP, HCP = Sh::HCP, NG = Sh::NG;
     constexpr int NP = Sh::NP, NPL = Sh::NPL, PITCH = Sh::PITCH, PLANE = Sh::PLANE, THREADS = Sh::THREADS, NWARP = Sh::NWARP;
@@ -443,7 +445,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
                 const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 const float4 ra = in_tile ? tf4[((8 * q + 2 * i) * SC + 4 * g) >> 2] : zero4;
                 const float4 rb = in_tile ? tf4[((8 * q + 2 * i + 1) * SC + 4 * g) >> 2] : zero4;
-                if (!INT_MODE) {
+                {   // float maps: the sign bits; integer maps: the bits above 2^24
                     neg |= (uint32_t)__float_as_int(ra.x) | (uint32_t)__float_as_int(ra.y) | (uint32_t)__float_as_int(ra.z) | (uint32_t)__float_as_int(ra.w);
                     neg |= (uint32_t)__float_as_int(rb.x) | (uint32_t)__float_as_int(rb.y) | (uint32_t)__float_as_int(rb.z) | (uint32_t)__float_as_int(rb.w);
                 }
@@ -484,6 +486,8 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         }
         if (!INT_MODE) {
             if (__any_sync(0xffffffffu, (int)(neg >> 31)) && lane == 0) ctr[4 + (iter & 1)] = 1;
+        } else if (cpi_flags != nullptr) {
+            if (__any_sync(0xffffffffu, (neg >> 24) != 0u) && lane == 0) atomicOr(cpi_flags + map / a.n_channels, (uint32_t)RDP_STATUS_MAP_RANGE);
         }
     }
     __syncthreads();

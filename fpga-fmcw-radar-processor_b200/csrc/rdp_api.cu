@@ -63,7 +63,7 @@ struct K3Launcher {
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(long long grid, size_t smem, cudaStream_t st, const float* rd_map, float* cfar_out,
                    uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
-                   const CUtensorMap* tmap);
+                   const CUtensorMap* tmap, uint32_t* cpi_flags);
 };
 
 template <class K>
@@ -229,13 +229,13 @@ struct K3Inst {
     }
     static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out,
                        uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
-                       const CUtensorMap* tmap) {
+                       const CUtensorMap* tmap, uint32_t* cpi_flags) {
         if (a.int_mode)
             RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, P0B, true>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
-                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
+                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap, cpi_flags);
         else
             RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, P0B, false>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
-                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap);
+                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap, cpi_flags);
     }
     static K3Launcher get() {
         return K3Launcher{TR, Sh::TC, Sh::SR, Sh::SC, Sh::smem_bytes(), &prepare, &launch};
@@ -244,7 +244,7 @@ struct K3Inst {
 struct K3Generic {
     static cudaError_t prepare(size_t, int* occ) { if (occ) *occ = 64; return cudaSuccess; }
     static void launch(long long grid, size_t, cudaStream_t st, const float* rd_map, float* cfar_out,
-                       uint32_t* det_bits, CfarArgs a, int, int, long long, int cap, const CUtensorMap*) {
+                       uint32_t* det_bits, CfarArgs a, int, int, long long, int cap, const CUtensorMap*, uint32_t*) {
         long long n_words = grid;   // grid carries the bitmask word count for the generic kernel, `use_tma` its CTA cap
         long long blocks = (n_words + 7) / 8;
         if (blocks > cap) blocks = cap;
@@ -500,7 +500,7 @@ int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, lon
 // K3 + K4 on n_cpi <= chunk maps-worth of CPIs: bitmask, then ordered compaction into dets / counts / status
 // (all three already offset to this chunk); cpi_label is the CPI index written into the records.
 int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp_det* dets, int* counts,
-             uint32_t* status, int cpi_label, int int_mode = 0, int n_range_rows = 0, const uint32_t* cpi_flags = nullptr) {
+             uint32_t* status, int cpi_label, int int_mode = 0, int n_range_rows = 0, uint32_t* cpi_flags = nullptr) {
     rdp_config c = h->cfg;                                 // by value: n_samples may be overridden (sharded maps)
     c.n_channels = h->map_channels;                        // maps per CPI (1 after channel combining)
     CfarArgs args = h->cfar;
@@ -534,7 +534,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     std::memset(&tmap, 0, sizeof(tmap));
     if (h->k3.trows == 0) {
         h->k3.launch(maps * c.n_samples * args.words_per_row, 0, h->cur, rd_map, cfar_out, h->det_bits, args, 0, 0,
-                     0, h->k3_grid_cap, &tmap);
+                     0, h->k3_grid_cap, &tmap, nullptr);
     } else {
         const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
         const int tiles_c = (c.n_chirps + h->k3.tcols - 1) / h->k3.tcols;
@@ -567,7 +567,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
             if (want > grid) grid = want;
         }
         h->k3.launch(grid, h->k3.smem, h->cur, rd_map, cfar_out, h->det_bits, args, tiles_r, tiles_c, n_tiles, use_tma,
-                     &tmap);
+                     &tmap, int_mode ? cpi_flags : nullptr);
     }
     stage_end(h);
     int rc = launch_check(h, "k3_cfar_kernel");
@@ -1169,9 +1169,10 @@ int rdp_cfar_stage_u32(rdp_handle* h, const uint32_t* mag_map, int32_t n_cpi, ui
     for (int base = 0; base < n_cpi; base += h->chunk) {
         const int n = (n_cpi - base) < h->chunk ? (n_cpi - base) : h->chunk;
         // the kernels move 32-bit words; in integer mode they are read as unsigned integers
+        RDP_CUDA(h, cudaMemsetAsync(h->cpi_flags[0], 0, sizeof(uint32_t) * (size_t)n, h->stream));   // RDP_STATUS_MAP_RANGE
         int rc = run_cfar(h, reinterpret_cast<const float*>(mag_map) + (size_t)base * cells, n,
                           cfar_out ? reinterpret_cast<float*>(cfar_out) + (size_t)base * cells : nullptr,
-                          dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base, 1);
+                          dets + (size_t)base * c.max_dets_per_cpi, n_dets + base, status + base, base, 1, 0, h->cpi_flags[0]);
         if (rc) return rc;
     }
     return RDP_OK;

@@ -25,6 +25,7 @@ ERRORS = {-1: "RDP_E_INVALID", -2: "RDP_E_NO_DEVICE", -3: "RDP_E_CUDA", -4: "RDP
 STATUS_DET_OVERFLOW = 1
 STATUS_WINDOW_SAT = 2          # arith="fixed": a window_multiplier output clipped (window_multiplier.vhd:151-158)
 STATUS_ADC_FULL_SCALE = 4      # int16 input: a sample of the CPI sits on a rail
+STATUS_MAP_RANGE = 8           # cfar_stage_fixed: a magnitude word >= 2^24 (outside the supported range)
 
 INPUT_FORMATS = {"int16": 0, "complex64": 1}
 MAG_MODES = {"amb": 0, "abs": 1, "pow": 2, "logpow": 3}

@@ -73,8 +73,10 @@ enum {
     RDP_STATUS_WINDOW_SAT = 1u << 1,    /* FIXED16: a window_multiplier output clipped to 16 bits somewhere in the
                                            CPI (saturation_flag, rtl/src/window_multiplier.vhd:151-158, which
                                            radar_core.vhd:447-456 ORs into status_overflow)                  */
-    RDP_STATUS_ADC_FULL_SCALE = 1u << 2 /* int16 input: a sample of the CPI sits on a rail (+32767 / -32768), i.e.
+    RDP_STATUS_ADC_FULL_SCALE = 1u << 2,/* int16 input: a sample of the CPI sits on a rail (+32767 / -32768), i.e.
                                            the ADC (or the synthetic generator) clipped before the path saw it */
+    RDP_STATUS_MAP_RANGE = 1u << 3      /* rdp_cfar_stage_u32: a magnitude word >= 2^24 was seen -- outside the
+                                           supported range, detections of this CPI may be missing               */
 };
 
 /*
@@ -242,7 +244,7 @@ int rdp_cfar_stage(rdp_handle* h, const float* rd_map, int32_t n_cpi, float* cfa
 
 /* Fixed-point CFAR stage: the map holds UNSIGNED INTEGER magnitudes (the 17-bit words of
  * magnitude_calc; HARD PRECONDITION: every word < 2^24 -- the pre-filter converts words to float and is only
- * conservative while that is exact; larger words silently lose detections) and every decision is the bit-exact integer
+ * conservative while that is exact; a CPI that breaks it gets RDP_STATUS_MAP_RANGE and may lose detections) and every decision is the bit-exact integer
  * arithmetic of rtl/src/os_cfar_2d.vhd:152-217 -- integer sum, mean = floor(sum / N_REF)
  * truncated to 17 bits, lo = mean >> 1, hi = (mean + lo) mod 2^17, exact product x_k * scale.
  * cfar_out (nullable) is the RTL's output word per cell: the CUT magnitude or 0.  Records carry

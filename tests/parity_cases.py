@@ -329,6 +329,18 @@ def case_cfar_fixed_point(make_core, n_range=64, n_doppler=64, seed=3, **kw):
     check_canonical(dets)
 
 
+def case_cfar_fixed_range_flag(make_core):
+    """rdp_cfar_stage_u32's hard precondition (words < 2^24) is checked on the device: RDP_STATUS_MAP_RANGE for exactly
+    the CPIs that break it."""
+    rng = np.random.default_rng(2)
+    m = rng.integers(0, 5000, size=(3, 1, 64, 64)).astype(np.uint32)
+    m[1, 0, 40, 7] = 1 << 24
+    m[2, 0, 0, 0] = (1 << 24) - 1
+    with make_core(n_range=64, n_doppler=64, max_cpis=3, max_dets_per_cpi=4096) as c:
+        _, _, status, _ = c.cfar_stage_fixed(m)
+    assert [int(x) & 8 for x in status] == [0, 8, 0]
+
+
 def case_cfar_fixed_tb_map(make_core):
     """rtl/src/tb_os_cfar_2d.vhd:42-75 map, (3,2,1,1), adaptive scale: bit-exact against the integer oracle,
     both targets detected (T1, :123-134)."""

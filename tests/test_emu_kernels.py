@@ -159,3 +159,7 @@ def test_adc_full_scale_flag(make_core):
 @pytest.mark.parametrize("fmt,mti,kw", [("int16", 0, dict()), ("complex64", 2, dict(mag_mode="pow", cfar_edges="raster"))])
 def test_combine_and_group(make_core, fmt, mti, kw):
     pc.case_combine_and_group(make_core, fmt=fmt, mti_mode=mti, **kw)
+
+
+def test_cfar_fixed_range_flag(make_core):
+    pc.case_cfar_fixed_range_flag(make_core)

@@ -133,6 +133,7 @@ def test_cfar_fixed_point_bit_exact(make_core, nr, nd, kw):
 
 def test_cfar_fixed_tb_map(make_core):
     pc.case_cfar_fixed_tb_map(make_core)
+    pc.case_cfar_fixed_range_flag(make_core)
 
 
 def test_cfar_fixed_rejects_untiled_window(make_core):
