@@ -292,6 +292,10 @@ struct StreamSlot {
     uint32_t* h_status = nullptr;
     int n_cpi = 0;
     bool busy = false;
+#ifndef RDP_EMU
+    cudaGraphExec_t graph = nullptr;        // the slot's kernel chain (K1 .. K5) captured once per n_cpi, replayed per submission
+    int graph_n_cpi = 0;
+#endif
 };
 
 struct rdp_handle {
@@ -331,6 +335,7 @@ struct rdp_handle {
     int knob_k3_debug_skip = 0, knob_k3_skew_ns = 0;
     int knob_k1_cluster = -1;       // RDP_K1_CLUSTER: -1 = automatic (sharded mode only), 0 / 1 = forced off / on
     int stream_spec_dets = kStreamSpecDets;
+    int knob_stream_graph = 1;      // RDP_STREAM_GRAPH: streaming submissions replay a CUDA graph of their kernel chain
     int k3_variant = 0;             // RDP_K3_VARIANT (tile shape / staging depth of the default CFAR window, A/B measurements)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved at create (NULL: manual tile loads)
     int cfar_tma = 0;               // last CFAR launch staged its tiles with TMA
@@ -790,6 +795,9 @@ void release(rdp_handle* h) {
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         if (sl.ev_out) cudaEventDestroy(sl.ev_out);
         if (sl.copy) cudaStreamDestroy(sl.copy);
+#ifndef RDP_EMU
+        if (sl.graph) cudaGraphExecDestroy(sl.graph);
+#endif
     }
     h->slots.clear();
     for (auto e : h->ev_copied) cudaEventDestroy(e);
@@ -852,6 +860,7 @@ int init_handle(rdp_handle* h) {
         if ((e = std::getenv("RDP_K3_DEBUG_SKIP"))) h->knob_k3_debug_skip = std::atoi(e);
         if ((e = std::getenv("RDP_K3_SKEW_NS"))) h->knob_k3_skew_ns = std::atoi(e);
         if ((e = std::getenv("RDP_STREAM_SPEC")) && std::atoi(e) > 0) h->stream_spec_dets = std::atoi(e);
+        if ((e = std::getenv("RDP_STREAM_GRAPH"))) h->knob_stream_graph = std::atoi(e);
     }
     // the FFT kernels (HBM-bound) run on `stream`, the CFAR kernels (ALU-bound) of the previous chunk on `cfar_stream`;
     // the FFT stream has the higher priority so that its CTAs are placed first whenever CFAR CTAs retire
@@ -1624,14 +1633,50 @@ int rdp_stream_submit(rdp_handle* h, int32_t slot, const void* cube, int32_t n_c
     RDP_CUDA(h, cudaMemcpyAsync(sl.d_in, cube, in_bytes, cudaMemcpyHostToDevice, sl.copy));
     RDP_CUDA(h, cudaEventRecord(sl.ev_in, sl.copy));
     RDP_CUDA(h, cudaStreamWaitEvent(h->stream, sl.ev_in, 0));
-    int rc = run_front(h, sl.d_in, n_cpi, h->map_scratch[0], h->cpi_flags[0]);
-    if (rc) return rc;
-    rc = run_cfar(h, h->map_scratch[0], n_cpi, nullptr, sl.d_dets, sl.d_counts, sl.d_status, 0, c.arith == RDP_ARITH_FIXED16, 0,
-                  h->cpi_flags[0]);
-    if (rc) return rc;
-    h->launches += 1;
-    RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, sl.d_dets, sl.d_counts, sl.d_packed, c.max_dets_per_cpi, 0, 0);
-    rc = launch_check(h, "k5_pack_dets_kernel");
+    // the kernel chain of one submission: front end, CFAR, compaction, pack -- all on the compute stream
+    auto chain = [&]() -> int {
+        int rc0 = run_front(h, sl.d_in, n_cpi, h->map_scratch[0], h->cpi_flags[0]);
+        if (rc0) return rc0;
+        rc0 = run_cfar(h, h->map_scratch[0], n_cpi, nullptr, sl.d_dets, sl.d_counts, sl.d_status, 0, c.arith == RDP_ARITH_FIXED16, 0,
+                       h->cpi_flags[0]);
+        if (rc0) return rc0;
+        h->launches += 1;
+        RDP_LAUNCH(k5_pack_dets_kernel, n_cpi, 256, 0, h->stream, sl.d_dets, sl.d_counts, sl.d_packed, c.max_dets_per_cpi, 0, 0);
+        return launch_check(h, "k5_pack_dets_kernel");
+    };
+    int rc = RDP_OK;
+#ifndef RDP_EMU
+    // Every buffer of the chain belongs to the slot or the handle, so the chain is the same from submission to
+    // submission: it is captured into a CUDA graph the first time a slot sees an n_cpi and replayed afterwards -- one
+    // launch instead of seven, tensor maps and launch parameters baked in (RDP_STREAM_GRAPH=0 turns it off; per-kernel
+    // stage timing needs the individual launches).
+    if (h->knob_stream_graph && !h->stage_timing) {
+        if (!sl.graph || sl.graph_n_cpi != n_cpi) {
+            if (sl.graph) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; }
+            const int64_t launches0 = h->launches;
+            cudaGraph_t g = nullptr;
+            RDP_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            rc = chain();
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+            if (rc == RDP_OK && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&sl.graph, g, 0);
+            if (g) cudaGraphDestroy(g);
+            h->launches = launches0;                                // counted per replay below
+            if (rc != RDP_OK || ce != cudaSuccess) {                 // fall back to plain launches for good
+                cudaGetLastError();
+                sl.graph = nullptr;
+                h->knob_stream_graph = 0;
+                rc = RDP_OK;
+            } else {
+                sl.graph_n_cpi = n_cpi;
+            }
+        }
+    }
+    if (h->knob_stream_graph && !h->stage_timing && sl.graph) {
+        RDP_CUDA(h, cudaGraphLaunch(sl.graph, h->stream));
+        h->launches += (c.arith == RDP_ARITH_FIXED16 ? 3 : 2) + 3 + 1 + (c.peak_group ? 1 : 0);   // front end, K3 + 2 x K4, K5, K3b
+    } else
+#endif
+    rc = chain();
     if (rc) return rc;
     RDP_CUDA(h, cudaEventRecord(sl.ev_done, h->stream));
     RDP_CUDA(h, cudaStreamWaitEvent(sl.copy, sl.ev_done, 0));
@@ -1688,6 +1733,9 @@ int rdp_stream_close(rdp_handle* h) {
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
         if (sl.ev_out) cudaEventDestroy(sl.ev_out);
         if (sl.copy) cudaStreamDestroy(sl.copy);
+#ifndef RDP_EMU
+        if (sl.graph) cudaGraphExecDestroy(sl.graph);
+#endif
     }
     h->slots.clear();
     return RDP_OK;

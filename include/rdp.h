@@ -180,7 +180,9 @@ typedef struct rdp_info {
  *   RDP_K3_CTAS=n         cap the persistent CFAR CTAs per SM;  RDP_K12_CTAS=n  the same for the two FFT kernels
  *   RDP_K1_CLUSTER=0|1    force the thread-block-cluster variant of the range stage off / on (default: only for the
  *                         peer-store corner turn of rdp_range_stage_scatter with 2048- / 4096-sample chirps)
- *   RDP_STREAM_SPEC=n     records per CPI a streaming slot copies back together with the counts (tests)            */
+ *   RDP_STREAM_SPEC=n     records per CPI a streaming slot copies back together with the counts (tests)
+ *   RDP_STREAM_GRAPH=0|1  streaming submissions replay a CUDA graph of their kernel chain (default 1)
+ *   RDP_K1_TMA=0|1        force the TMA tile store of the range stage off / on (default: on for int16 input)       */
 typedef struct rdp_handle rdp_handle;
 
 /* Fills *cfg with the reference defaults (radar_core.vhd:12-20: 1024 x 128, CFAR 4/4/2/1,
