@@ -125,6 +125,8 @@ struct BfpFuse {
     int mag_out;
 };
 
+// NB > 0: n == 64 * NB (NB butterflies per lane and stage, kept in registers); NB == 0: any n, butterflies recomputed
+template <int NB>
 __global__ void __launch_bounds__(256)
 kf_bfp_fft_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int* __restrict__ exps,
                   const uint32_t* __restrict__ tw, int n, int log2n, long long n_frames, int warps_per_cta, BfpFuse fu) {
@@ -161,23 +163,49 @@ kf_bfp_fft_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, i
         int e = 0;
         for (int s = 0; s < log2n; ++s) {
             const int half = n >> (s + 1);
-            int g = 0;
-            for (int j = lane; j < n / 2; j += 32) {
-                const int pos = j & (half - 1), i0 = ((j >> (log2n - 1 - s)) << (log2n - s)) + pos;
-                const BfpButterfly o = bfp_butterfly(fb[i0], fb[i0 + half], __ldg(tw + (pos << s)));
-                const int m1 = iabs_(o.sr) > iabs_(o.si) ? iabs_(o.sr) : iabs_(o.si);
-                const int m2 = iabs_(o.pr) > iabs_(o.pi) ? iabs_(o.pr) : iabs_(o.pi);
-                g = g > m1 ? g : m1;
-                g = g > m2 ? g : m2;
-            }
-            g = __reduce_max_sync(0xffffffffu, g);
             int sh = 0;
-            while (((g + (1 << sh) - 1) >> sh) > 32767) ++sh;
-            for (int j = lane; j < n / 2; j += 32) {                 // every butterfly rewrites its own two words
-                const int pos = j & (half - 1), i0 = ((j >> (log2n - 1 - s)) << (log2n - s)) + pos;
-                const BfpButterfly o = bfp_butterfly(fb[i0], fb[i0 + half], __ldg(tw + (pos << s)));
-                fb[i0] = make_word((int)cround_ll(o.sr, sh), (int)cround_ll(o.si, sh));
-                fb[i0 + half] = make_word((int)cround_ll(o.pr, sh), (int)cround_ll(o.pi, sh));
+            if (NB > 0) {
+                // n = 64 NB points: the lane's NB butterflies of the stage stay in registers between the pass that finds
+                // the frame's largest component and the one that shifts -- each butterfly is computed once
+                BfpButterfly o[NB > 0 ? NB : 1];
+                int i0s[NB > 0 ? NB : 1];
+                int g = 0;
+                RDP_UNROLL
+                for (int q = 0; q < NB; ++q) {
+                    const int j = lane + 32 * q;
+                    const int pos = j & (half - 1);
+                    i0s[q] = ((j >> (log2n - 1 - s)) << (log2n - s)) + pos;
+                    o[q] = bfp_butterfly(fb[i0s[q]], fb[i0s[q] + half], __ldg(tw + (pos << s)));
+                    const int m1 = iabs_(o[q].sr) > iabs_(o[q].si) ? iabs_(o[q].sr) : iabs_(o[q].si);
+                    const int m2 = iabs_(o[q].pr) > iabs_(o[q].pi) ? iabs_(o[q].pr) : iabs_(o[q].pi);
+                    g = g > m1 ? g : m1;
+                    g = g > m2 ? g : m2;
+                }
+                g = __reduce_max_sync(0xffffffffu, g);
+                while (((g + (1 << sh) - 1) >> sh) > 32767) ++sh;
+                RDP_UNROLL
+                for (int q = 0; q < NB; ++q) {
+                    fb[i0s[q]] = make_word((int)cround_ll(o[q].sr, sh), (int)cround_ll(o[q].si, sh));
+                    fb[i0s[q] + half] = make_word((int)cround_ll(o[q].pr, sh), (int)cround_ll(o[q].pi, sh));
+                }
+            } else {
+                int g = 0;
+                for (int j = lane; j < n / 2; j += 32) {
+                    const int pos = j & (half - 1), i0 = ((j >> (log2n - 1 - s)) << (log2n - s)) + pos;
+                    const BfpButterfly o = bfp_butterfly(fb[i0], fb[i0 + half], __ldg(tw + (pos << s)));
+                    const int m1 = iabs_(o.sr) > iabs_(o.si) ? iabs_(o.sr) : iabs_(o.si);
+                    const int m2 = iabs_(o.pr) > iabs_(o.pi) ? iabs_(o.pr) : iabs_(o.pi);
+                    g = g > m1 ? g : m1;
+                    g = g > m2 ? g : m2;
+                }
+                g = __reduce_max_sync(0xffffffffu, g);
+                while (((g + (1 << sh) - 1) >> sh) > 32767) ++sh;
+                for (int j = lane; j < n / 2; j += 32) {                 // every butterfly rewrites its own two words
+                    const int pos = j & (half - 1), i0 = ((j >> (log2n - 1 - s)) << (log2n - s)) + pos;
+                    const BfpButterfly o = bfp_butterfly(fb[i0], fb[i0 + half], __ldg(tw + (pos << s)));
+                    fb[i0] = make_word((int)cround_ll(o.sr, sh), (int)cround_ll(o.si, sh));
+                    fb[i0 + half] = make_word((int)cround_ll(o.pr, sh), (int)cround_ll(o.pi, sh));
+                }
             }
             __syncwarp();
             e += sh;

@@ -665,14 +665,27 @@ int launch_bfp(rdp_handle* h, const uint32_t* in, uint32_t* out, int* exps, cons
     while ((1 << log2n) < n) ++log2n;
     const int wpc = 8;                                            // one warp per frame, 8 frames in flight per CTA
     const size_t smem = (size_t)wpc * n * sizeof(uint32_t);
-#ifndef RDP_EMU
-    if (smem > 48 * 1024) RDP_CUDA(h, cudaFuncSetAttribute(kf_bfp_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
     long long blocks = (n_frames + wpc - 1) / wpc;
     const long long cap = (long long)h->sm_count * (smem > 64 * 1024 ? 1 : (smem > 32 * 1024 ? 3 : 6));
     if (blocks > cap) blocks = cap;
     h->launches += 1;
-    RDP_LAUNCH(kf_bfp_fft_kernel, (unsigned)blocks, 256, smem, h->cur, in, out, exps, tw, n, log2n, n_frames, wpc, fu);
+#ifndef RDP_EMU
+#define RDP_BFP_ATTR(NB) if (smem > 48 * 1024) RDP_CUDA(h, cudaFuncSetAttribute(kf_bfp_fft_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#else
+#define RDP_BFP_ATTR(NB)
+#endif
+#define RDP_BFP_CASE(NB) \
+    { RDP_BFP_ATTR(NB); RDP_LAUNCH(kf_bfp_fft_kernel<NB>, (unsigned)blocks, 256, smem, h->cur, in, out, exps, tw, n, log2n, n_frames, wpc, fu); }
+    switch (n) {                                                  // 64 ... 1024 points: the stage's butterflies stay in registers
+        case 64: RDP_BFP_CASE(1) break;
+        case 128: RDP_BFP_CASE(2) break;
+        case 256: RDP_BFP_CASE(4) break;
+        case 512: RDP_BFP_CASE(8) break;
+        case 1024: RDP_BFP_CASE(16) break;
+        default: RDP_BFP_CASE(0) break;
+    }
+#undef RDP_BFP_CASE
+#undef RDP_BFP_ATTR
     return launch_check(h, "kf_bfp_fft_kernel");
 }
 
