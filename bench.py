@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--arith", default="float32", choices=["float32", "fixed"],
                     help="fixed = the 16-bit word-for-word chain (profiling only; use with --no-cpu --no-e2e)")
-    ap.add_argument("--combine", default="none", choices=["none", "nci"],
+    ap.add_argument("--combine", default="none", choices=["none", "nci", "beams"],
                     help="nci = non-coherent integration over the channels before the CFAR (optional stage; profiling only)")
     ap.add_argument("--peak-group", action="store_true", help="peak grouping of the detections (optional stage; profiling only)")
     ap.add_argument("--shape", default="automotive", choices=sorted(SHAPES), help="profiling only; default = the bench workload")
@@ -274,7 +274,8 @@ def main():
         t = st_t[name]
         if t["launches"]:
             avg_ms = t["ms"] / t["launches"]
-            cells_per_launch = 2.0 * n_cpi * (CELLS // N_CH if (name == "cfar" and args.combine == "nci") else CELLS) / t["launches"]
+            map_ch = {"nci": 1, "beams": 1 << (N_CH - 1).bit_length()}.get(args.combine, N_CH)      # maps per CPI the CFAR sees
+            cells_per_launch = 2.0 * n_cpi * (CELLS // N_CH * map_ch if name == "cfar" else CELLS) / t["launches"]
             gbs = cells_per_launch * bpc / (avg_ms * 1e-3) / 1e9
             stages[name] = {"ms_total_per_step": t["ms"] / 2.0, "launches_per_step": t["launches"] // 2,
                             "avg_launch_ms": avg_ms, "alg_bytes_per_cell": bpc, "achieved_gbs": gbs, "frac": gbs / peak}
@@ -429,7 +430,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.arith == "float32" else "int16 block floating point",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.fmt, n_cpi) + ("" if args.arith == "float32" else "_fixed16") +
-                                       ("" if args.combine == "none" else "_nci") + ("_peakgroup" if args.peak_group else ""), "cpis_per_gpu_per_step": n_cpi,
+                                       ("" if args.combine == "none" else "_" + args.combine) + ("_peakgroup" if args.peak_group else ""), "cpis_per_gpu_per_step": n_cpi,
                            "unique_cpis": int(uniq.shape[0]), "chunk_cpis": info["chunk_cpis"],
                            "cfar": ("ref 8/8 guard 4/2" if "cfar_ref_r" in CFAR_KW else "ref 4/4 guard 2/1") + " rank 75% adaptive scale 2/4/6, as_built axes, zero edges",
                            "l2": "input batch (%.1f GB) far exceeds the 126 MB L2; no flush needed" % (n_cpi * per_cpi / 1e9),

@@ -37,12 +37,19 @@ __device__ __forceinline__ float magnitude(float2 z) {
     return 10.0f * log10f(fmaxf(p, 1e-30f));
 }
 
-template <class Plan, int MAG, bool COMBINE = false>
+// COMBINE: 0 = one map per channel; 1 = non-coherent integration (above); 2 = coherent beams of a uniform linear array:
+// the n_combine channels of one (CPI, range line) are summed with the steering phases exp(-j 2 pi beam c / n_beams)
+// BEFORE the transform (it is linear, so this equals an angle FFT across the channels after it) and ONE Doppler
+// transform per beam follows; output lines are enumerated (cpi, range, beam) with the beam fastest, so that the
+// n_beams passes over a line's channels hit L1 / L2, and land in [cpi][beam][range][doppler].
+template <class Plan, int MAG, int COMBINE = 0>
 __global__ void __launch_bounds__(K2Shape<Plan>::THREADS)
 k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                   const float* __restrict__ window, const float2* __restrict__ twtab,
-                  long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int n_combine, int n_range) {
-    // COMBINE: n_rows counts OUTPUT lines (cpi, range); input line of channel c = (cpi * n_combine + c) * n_range + range
+                  long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int n_combine, int n_range,
+                  int n_beams, const float2* __restrict__ steer) {
+    // COMBINE 1: n_rows counts OUTPUT lines (cpi, range); COMBINE 2: (cpi, range, beam).
+    // Input line of channel c = (cpi * n_combine + c) * n_range + range.  steer[m] = exp(-j 2 pi m / n_beams).
     constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
     constexpr int G = K2Shape<Plan>::G;
     using P0 = typename Plan::P0;
@@ -62,12 +69,13 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
     int parity = 0;
     const long long stride = (long long)gridDim.x * G;
 
-    // software pipeline: the next range line's samples are in flight during the butterflies
+    // software pipeline: the next line's samples are in flight during the butterflies
     float2 raw[E];
+    auto line_of = [&](long long row) -> long long { return COMBINE == 2 ? row / n_beams : row; };   // (cpi, range) index
     auto in_row = [&](long long row, int ch) -> long long {
-        if (!COMBINE) return row;
-        const long long cpi = row / n_range;
-        return (cpi * n_combine + ch) * n_range + (row - cpi * n_range);
+        if (COMBINE == 0) return row;
+        const long long line = line_of(row), cpi = line / n_range;
+        return (cpi * n_combine + ch) * n_range + (line - cpi * n_range);
     };
     auto fetch = [&](long long row, int ch) {
         const bool ok = row < n_rows;
@@ -84,16 +92,22 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
     for (long long row0 = (long long)blockIdx.x * G; row0 < n_rows; row0 += stride) {
         const long long row = row0 + gid;
         const bool active = row < n_rows;
-        float macc[COMBINE ? E : 1];
-        if (COMBINE) {
+        const int beam = COMBINE == 2 ? (int)((active ? row : 0) % n_beams) : 0;
+        float macc[COMBINE == 1 ? E : 1];                            // COMBINE 1: sum of the channels' magnitudes
+        float2 bacc[COMBINE == 2 ? E : 1];                           // COMBINE 2: steered sum of the channels' samples
+        if (COMBINE == 1) {
             RDP_UNROLL
-            for (int i = 0; i < (COMBINE ? E : 1); ++i) macc[i] = 0.0f;
+            for (int i = 0; i < (COMBINE == 1 ? E : 1); ++i) macc[i] = 0.0f;
+        }
+        if (COMBINE == 2) {
+            RDP_UNROLL
+            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) bacc[i] = make_float2(0.0f, 0.0f);
         }
       for (int ch = 0; ch < (COMBINE ? n_combine : 1); ++ch) {
-        float2 v[E];
+        float2 v[E];                                     // the line's samples after the notch, before the window
         if (mti_mode == 0) {
             RDP_UNROLL
-            for (int i = 0; i < E; ++i) v[i] = make_float2(raw[i].x * wv[i], raw[i].y * wv[i]);
+            for (int i = 0; i < E; ++i) v[i] = raw[i];
         } else {                                         // doppler_notch.vhd:72-93, zero initial state (:99-102)
             const float2* src = x_rc + in_row(active ? row : 0, ch) * N;
             RDP_UNROLL
@@ -109,28 +123,41 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                         const float2 d2 = (active && n >= 2) ? __ldg(src + n - 2) : make_float2(0.f, 0.f);
                         s = make_float2(s.x - 2.0f * d1.x + d2.x, s.y - 2.0f * d1.y + d2.y);
                     }
-                    const float w = wv[b * P0::R + r];
-                    v[b * P0::R + r] = make_float2(s.x * w, s.y * w);
+                    v[b * P0::R + r] = s;
                 }
             }
         }
         if (COMBINE && ch + 1 < n_combine) fetch(row, ch + 1);
         else fetch(row + stride, 0);
-        Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
-        if (COMBINE) {
+        if (COMBINE == 2) {
+            const float2 ph = __ldg(steer + ((beam * ch) & (n_beams - 1)));
             RDP_UNROLL
-            for (int i = 0; i < (COMBINE ? E : 1); ++i) macc[i] += magnitude<MAG>(v[i]);
+            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) bacc[i] = cadd(bacc[i], cmul(v[i], ph));
+            if (ch + 1 < n_combine) continue;
+            RDP_UNROLL
+            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) v[i] = bacc[i];
+        }
+        RDP_UNROLL
+        for (int i = 0; i < E; ++i) v[i] = make_float2(v[i].x * wv[i], v[i].y * wv[i]);
+        Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
+        if (COMBINE == 1) {
+            RDP_UNROLL
+            for (int i = 0; i < (COMBINE == 1 ? E : 1); ++i) macc[i] += magnitude<MAG>(v[i]);
             if (ch + 1 < n_combine) continue;
         }
         if (active) {
             // sharded mode: every map of rows_per_map lines is written with pad_rows halo lines above and below
-            const long long orow = rows_per_map > 0 ? row + (2 * (row / rows_per_map) + 1) * pad_rows : row;
+            long long orow = rows_per_map > 0 ? row + (2 * (row / rows_per_map) + 1) * pad_rows : row;
+            if (COMBINE == 2) {                                      // (cpi, range, beam) -> [cpi][beam][range]
+                const long long line = row / n_beams, cpi = line / n_range;
+                orow = (cpi * n_beams + beam) * n_range + (line - cpi * n_range);
+            }
             float* dst = rd_map + orow * N;
             RDP_UNROLL
             for (int b = 0; b < PL::NB; ++b) {
                 RDP_UNROLL
                 for (int r = 0; r < PL::R; ++r)
-                    dst[PL::out_index(tid, b, r)] = COMBINE ? macc[b * PL::R + r] : magnitude<MAG>(v[b * PL::R + r]);
+                    dst[PL::out_index(tid, b, r)] = COMBINE == 1 ? macc[b * PL::R + r] : magnitude<MAG>(v[b * PL::R + r]);
             }
         }
       }   // channels

@@ -54,7 +54,8 @@ struct K2Launcher {
     size_t smem;
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(int grid, size_t smem, cudaStream_t st, const float2* x_rc, float* rd_map, const float* win,
-                   const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int n_combine, int n_range);
+                   const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int combine, int n_combine,
+                   int n_range, int n_beams, const float2* steer);
 };
 struct K3Launcher {
     int trows, tcols;            // 0,0 => generic kernel
@@ -154,18 +155,26 @@ struct K1Inst {
 template <class Plan, int MAG>
 struct K2Inst {
     static cudaError_t prepare(size_t s, int* occ) {
-        cudaError_t e = prepare_kernel(k2_doppler_kernel<Plan, MAG, true>, K2Shape<Plan>::THREADS, s, nullptr);
+        cudaError_t e = prepare_kernel(k2_doppler_kernel<Plan, MAG, 1>, K2Shape<Plan>::THREADS, s, nullptr);
         if (e != cudaSuccess) return e;
-        return prepare_kernel(k2_doppler_kernel<Plan, MAG, false>, K2Shape<Plan>::THREADS, s, occ);
+        e = prepare_kernel(k2_doppler_kernel<Plan, MAG, 2>, K2Shape<Plan>::THREADS, s, nullptr);
+        if (e != cudaSuccess) return e;
+        return prepare_kernel(k2_doppler_kernel<Plan, MAG, 0>, K2Shape<Plan>::THREADS, s, occ);
     }
     static void launch(int grid, size_t s, cudaStream_t st, const float2* x_rc, float* rd_map, const float* win,
-                       const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int n_combine, int n_range) {
-        if (n_combine > 0)             // non-coherent integration over n_combine channels: n_rows counts OUTPUT lines
-            RDP_LAUNCH((k2_doppler_kernel<Plan, MAG, true>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
-                       n_rows, mti_mode, rows_per_map, pad_rows, n_combine, n_range);
+                       const float2* tw, long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int combine, int n_combine,
+                       int n_range, int n_beams, const float2* steer) {
+        // combine 1: non-coherent integration over n_combine channels, n_rows counts OUTPUT lines (cpi, range);
+        // combine 2: coherent beams, n_rows counts (cpi, range, beam)
+        if (combine == RDP_COMBINE_NCI)
+            RDP_LAUNCH((k2_doppler_kernel<Plan, MAG, 1>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
+                       n_rows, mti_mode, rows_per_map, pad_rows, n_combine, n_range, 1, steer);
+        else if (combine == RDP_COMBINE_BEAMS)
+            RDP_LAUNCH((k2_doppler_kernel<Plan, MAG, 2>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
+                       n_rows, mti_mode, rows_per_map, pad_rows, n_combine, n_range, n_beams, steer);
         else
-            RDP_LAUNCH((k2_doppler_kernel<Plan, MAG, false>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
-                       n_rows, mti_mode, rows_per_map, pad_rows, 1, n_range);
+            RDP_LAUNCH((k2_doppler_kernel<Plan, MAG, 0>), grid, K2Shape<Plan>::THREADS, s, st, x_rc, rd_map, win, tw,
+                       n_rows, mti_mode, rows_per_map, pad_rows, 1, n_range, 1, steer);
     }
     static K2Launcher get() {
         return K2Launcher{Plan::T, K2Shape<Plan>::G, K2Shape<Plan>::smem_bytes(), &prepare, &launch};
@@ -350,7 +359,9 @@ struct rdp_handle {
     int* rom_dev = nullptr;         // mirrored Q15 Hamming coefficients of the last fixed-point window length (tap)
     int rom_n = 0;
     uint32_t* sat_dev = nullptr;
-    int map_channels = 1;          // maps per CPI the CFAR stage sees: n_channels, or 1 with combine = NCI
+    int map_channels = 1;          // maps per CPI the CFAR stage sees: n_channels, 1 with combine = NCI, n_beams with BEAMS
+    int n_beams = 1;               // combine = BEAMS: smallest power of two >= n_channels
+    float2* steer = nullptr;       // exp(-j 2 pi m / n_beams), m < n_beams
     uint32_t* det_bits2 = nullptr; // peak_group: the grouped bitmask (same shape as det_bits)
     size_t det_bits2_cap = 0;
     uint32_t* cpi_flags[2] = {nullptr, nullptr};   // [chunk] status bits raised before the CFAR stage, by chunk parity
@@ -394,7 +405,11 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 size_t in_bytes_per_sample(const rdp_config& c) { return c.input_format == RDP_IN_INT16_IQ ? 4 : 8; }
 size_t cells_per_cpi(const rdp_config& c) { return (size_t)c.n_channels * c.n_chirps * c.n_samples; }
 // cells of the range-Doppler map(s) of one CPI: one map per channel, or a single combined map (combine = NCI)
-size_t map_cells_per_cpi(const rdp_config& c) { return (size_t)(c.combine == RDP_COMBINE_NCI ? 1 : c.n_channels) * c.n_chirps * c.n_samples; }
+int beams_for(int n_channels) { int b = 1; while (b < n_channels) b <<= 1; return b; }
+int map_channels_of(const rdp_config& c) {
+    return c.combine == RDP_COMBINE_NCI ? 1 : (c.combine == RDP_COMBINE_BEAMS ? beams_for(c.n_channels) : c.n_channels);
+}
+size_t map_cells_per_cpi(const rdp_config& c) { return (size_t)map_channels_of(c) * c.n_chirps * c.n_samples; }
 
 template <class T>
 int dev_alloc(rdp_handle* h, T** p, size_t count) {
@@ -490,14 +505,14 @@ int run_range(rdp_handle* h, const void* cube, int n_cpi, float2* x_rc, const K1
 int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, long long rows_override = -1,
                 int rows_per_map = 0, int pad_rows = 0) {
     const rdp_config& c = h->cfg;
-    const bool nci = c.combine == RDP_COMBINE_NCI && rows_override < 0;
-    const long long rows = rows_override >= 0 ? rows_override : (long long)n_cpi * (nci ? 1 : c.n_channels) * c.n_samples;
+    const int combine = rows_override < 0 ? c.combine : RDP_COMBINE_NONE;
+    const long long rows = rows_override >= 0 ? rows_override : (long long)n_cpi * h->map_channels * c.n_samples;
     if (rows == 0) return RDP_OK;
     long long blocks = (rows + h->k2.G - 1) / h->k2.G;
     int grid = (int)(blocks < h->k2_grid_cap ? blocks : h->k2_grid_cap);
     stage_begin(h, 1);
     h->k2.launch(grid, h->k2.smem, h->cur, x_rc, rd_map, h->win_d, h->tw_d, rows, c.mti_mode, rows_per_map, pad_rows,
-                 nci ? c.n_channels : 0, c.n_samples);
+                 combine, c.n_channels, c.n_samples, h->n_beams, h->steer);
     stage_end(h);
     return launch_check(h, "k2_doppler_kernel");
 }
@@ -782,7 +797,7 @@ int check_cfg(const rdp_config* c) {
     if (c->max_cpis < 1) return fail(nullptr, RDP_E_INVALID, "max_cpis must be >= 1");
     if (c->chunk_cpis < 0) return fail(nullptr, RDP_E_INVALID, "chunk_cpis must be >= 0");
     if (c->arith != RDP_ARITH_FLOAT32 && c->arith != RDP_ARITH_FIXED16) return fail(nullptr, RDP_E_INVALID, "unknown arith %d", c->arith);
-    if (c->combine != RDP_COMBINE_NONE && c->combine != RDP_COMBINE_NCI) return fail(nullptr, RDP_E_INVALID, "unknown combine %d", c->combine);
+    if (c->combine < RDP_COMBINE_NONE || c->combine > RDP_COMBINE_BEAMS) return fail(nullptr, RDP_E_INVALID, "unknown combine %d", c->combine);
     if (c->peak_group != 0 && c->peak_group != 1) return fail(nullptr, RDP_E_INVALID, "peak_group must be 0 or 1");
     if (c->combine != RDP_COMBINE_NONE && c->arith == RDP_ARITH_FIXED16)
         return fail(nullptr, RDP_E_INVALID, "channel combining is not part of the RTL chain: use arith FLOAT32");
@@ -821,7 +836,7 @@ void release(rdp_handle* h) {
     if (h->t1) cudaEventDestroy(h->t1);
     void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
                     h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->rom_dev, h->sat_dev, h->trk_state, h->counts, h->status, h->dets, h->packed, h->l2_flush,
-                    h->cpi_flags[0], h->cpi_flags[1], h->det_bits2, h->rom_r, h->rom_d, h->btw_r, h->btw_d, h->exp_r, h->exp_d, h->btw_tap};
+                    h->cpi_flags[0], h->cpi_flags[1], h->det_bits2, h->steer, h->rom_r, h->rom_d, h->btw_r, h->btw_d, h->exp_r, h->exp_d, h->btw_tap};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -924,7 +939,19 @@ int init_handle(rdp_handle* h) {
 
     // CFAR geometry in physical axes (os_cfar_2d.vhd:41-47)
     CfarArgs& a = h->cfar;
-    h->map_channels = c.combine == RDP_COMBINE_NCI ? 1 : c.n_channels;
+    h->map_channels = map_channels_of(c);
+    h->n_beams = beams_for(c.n_channels);
+    if (c.combine == RDP_COMBINE_BEAMS) {
+        std::vector<float2> st((size_t)h->n_beams);
+        const double pi = 3.14159265358979323846;
+        for (int m = 0; m < h->n_beams; ++m) {
+            const double ang = -2.0 * pi * (double)m / (double)h->n_beams;
+            st[(size_t)m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        int rc0 = dev_alloc(h, &h->steer, st.size());
+        if (rc0) return rc0;
+        RDP_CUDA(h, cudaMemcpy(h->steer, st.data(), sizeof(float2) * st.size(), cudaMemcpyHostToDevice));
+    }
     a.n_range = c.n_samples; a.n_doppler = c.n_chirps; a.n_channels = h->map_channels;
     if (c.cfar_axes == RDP_AXES_AS_BUILT) {
         a.half_l = c.cfar_ref_d + c.cfar_guard_d; a.guard_l = c.cfar_guard_d;
@@ -1009,14 +1036,14 @@ int init_handle(rdp_handle* h) {
     rc = dev_alloc(h, &h->x_rc, (size_t)chunk * cells_per_cpi(c));
     if (rc) return rc;
     for (int i = 0; i < 2; ++i) {
-        rc = dev_alloc(h, &h->map_scratch[i], (size_t)chunk * cells_per_cpi(c));
+        rc = dev_alloc(h, &h->map_scratch[i], (size_t)chunk * map_cells_per_cpi(c));
         if (rc) return rc;
     }
-    rc = dev_alloc(h, &h->det_bits, (size_t)chunk * c.n_channels * c.n_samples * h->cfar.words_per_row);
+    rc = dev_alloc(h, &h->det_bits, (size_t)chunk * h->map_channels * c.n_samples * h->cfar.words_per_row);
     if (rc) return rc;
-    rc = dev_alloc(h, &h->row_off, (size_t)chunk * c.n_channels * c.n_samples);
+    rc = dev_alloc(h, &h->row_off, (size_t)chunk * h->map_channels * c.n_samples);
     if (rc) return rc;
-    h->cfar_rows_cap = (size_t)chunk * c.n_channels * c.n_samples;
+    h->cfar_rows_cap = (size_t)chunk * h->map_channels * c.n_samples;
     rc = dev_alloc(h, &h->counts, (size_t)c.max_cpis);
     if (rc) return rc;
     rc = dev_alloc(h, &h->status, (size_t)c.max_cpis);

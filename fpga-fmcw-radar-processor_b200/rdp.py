@@ -32,7 +32,7 @@ MAG_MODES = {"amb": 0, "abs": 1, "pow": 2, "logpow": 3}
 CFAR_AXES = {"as_built": 0, "as_named": 1}
 CFAR_EDGES = {"zero": 0, "raster": 1}
 ARITH = {"float32": 0, "fixed": 1}
-COMBINE = {"none": 0, "nci": 1}
+COMBINE = {"none": 0, "nci": 1, "beams": 2}
 
 # one reported track; layout == struct rdp_track
 TRACK_DTYPE = np.dtype([(n, "<i4") for n in ("cpi", "channel", "id", "range_q2", "doppler_q2", "vel_r", "vel_d",
@@ -227,7 +227,11 @@ class RadarCore:
         self.n_range, self.n_doppler, self.n_channels = n_range, n_doppler, n_channels
         self.input_format = input_format
         self.arith = arith
-        self.map_channels = 1 if combine == "nci" else n_channels           # maps per CPI the CFAR stage sees
+        n_beams = 1
+        while n_beams < n_channels:
+            n_beams <<= 1
+        # maps per CPI the CFAR stage sees: one per channel, one combined map (nci), or one per beam (beams)
+        self.map_channels = {"nci": 1, "beams": n_beams}.get(combine, n_channels)
         self.map_dtype = np.uint32 if arith == "fixed" else np.float32     # words of the range-Doppler map
         self.max_dets_per_cpi, self.max_cpis = max_dets_per_cpi, max_cpis
         self._pinned = []
@@ -411,7 +415,7 @@ class RadarCore:
         x_rc = np.ascontiguousarray(x_rc, dtype=np.complex64).reshape(-1, self.n_channels, self.n_range, self.n_doppler)
         n_cpi = x_rc.shape[0]
         d_in = self.device_buffer(x_rc.nbytes).upload(x_rc)
-        d_out = self.device_buffer(n_cpi * self.cells_per_cpi * 4)
+        d_out = self.device_buffer(n_cpi * self.map_channels * self.n_range * self.n_doppler * 4)
         try:
             self._check(self.lib.rdp_doppler_stage(self.h, d_in.ptr, n_cpi, d_out.ptr))
             self.sync()

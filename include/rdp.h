@@ -55,8 +55,12 @@ enum { RDP_ARITH_FLOAT32 = 0, RDP_ARITH_FIXED16 = 1 };
  * row 3): NONE = one range-Doppler map and one CFAR per channel; NCI = non-coherent integration, the magnitudes (in
  * the configured mag_mode; RDP_MAG_POW gives the classical power integration) of the n_channels channels of a CPI
  * are added cell by cell (float32, channel 0 first) inside the Doppler stage and the CFAR runs on the ONE combined
- * map: rd_map is then [n_cpi][1][range][doppler] and every record has channel = 0.  FLOAT32 arithmetic only.     */
-enum { RDP_COMBINE_NONE = 0, RDP_COMBINE_NCI = 1 };
+ * map: rd_map is then [n_cpi][1][range][doppler] and every record has channel = 0.  FLOAT32 arithmetic only.
+ * BEAMS = coherent digital beamforming of a uniform linear array: n_beams = the smallest power of two >= n_channels,
+ * beam b = sum over channels c of x_c * exp(-j 2 pi b c / n_beams), formed on the range-major intermediate inside the
+ * Doppler stage (the transform is linear: steering before the Doppler FFT equals an angle FFT across the channels after
+ * it); rd_map is [n_cpi][n_beams][range][doppler], the CFAR runs per beam and every record's channel = its beam.   */
+enum { RDP_COMBINE_NONE = 0, RDP_COMBINE_NCI = 1, RDP_COMBINE_BEAMS = 2 };
 /* cfar_axes: AS_BUILT = the RTL's *_RANGE generics act along Doppler and *_DOPPLER along
  * range (rtl/src/os_cfar_2d.vhd:140-146,157-159); AS_NAMED = what the names say.        */
 enum { RDP_AXES_AS_BUILT = 0, RDP_AXES_AS_NAMED = 1 };
@@ -235,7 +239,8 @@ int rdp_process_fixed_device(rdp_handle* h, const void* cube, int32_t n_cpi, uin
  *   range stage   = window_multiplier + range FFT + corner_turner  (radar_core.vhd:267-327)
  *                   cube -> x_rc [n_cpi][channel][range][chirp] complex64
  *   doppler stage = doppler_notch + window_multiplier + Doppler FFT + magnitude_calc (:329-374)
- *                   x_rc -> rd_map [n_cpi][channel][range][doppler] float32
+ *                   x_rc -> rd_map [n_cpi][channel][range][doppler] float32 ([n_cpi][1] / [n_cpi][n_beams] maps per
+ *                   CPI with combine = NCI / BEAMS: size the buffer for them)
  *   cfar stage    = os_cfar_2d + non-zero filter + coordinates (:376-418)
  *                   rd_map -> detections; cfar_out (nullable) is the RTL's dense output
  *                   word per cell: CUT magnitude or 0.                                    */

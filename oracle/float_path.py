@@ -29,6 +29,7 @@ DEFAULTS = dict(
     window_gain=1.0,       # 1.0, or 2.0 to mirror the as-built x2 gain of the RTL window
     # optional stages that are NOT in the reference (the RTL has one channel and no grouping):
     combine="none",        # none | nci: non-coherent integration, magnitudes of all channels added before the CFAR
+                           # | beams: coherent beams of a uniform linear array (angle DFT over the channels)
     peak_group=False,      # keep a detection only if no neighbouring detection (8-neighbourhood) is larger
 )
 
@@ -241,7 +242,19 @@ def process_cpi(frame: np.ndarray, **kw):
     if frame.ndim == (2 if cplx else 3):
         frame = frame[None]
     p = params(**kw)
-    m = rd_map(frame, **kw)
+    if p["combine"] == "beams":
+        # n_beams = smallest power of two >= channels; beam b = sum_c x_c exp(-j 2 pi b c / n_beams) on the range-major
+        # intermediate (linear: the same as an angle DFT across the channels after the Doppler transform)
+        x = range_stage(frame, p["window_gain"])                 # [channel, range, chirp]
+        n_ch = x.shape[0]
+        n_beams = 1
+        while n_beams < n_ch:
+            n_beams <<= 1
+        steer = np.exp(-2j * np.pi * np.outer(np.arange(n_beams), np.arange(n_ch)) / n_beams)
+        y = np.einsum("bc,crk->brk", steer, x)
+        m = doppler_stage(y, p["mti_mode"], p["mag_mode"], p["window_gain"])
+    else:
+        m = rd_map(frame, **kw)
     if p["combine"] == "nci":                                   # one combined map per CPI, channel index 0
         m = m.sum(axis=0, keepdims=True)
     m = m.astype(np.float32)

@@ -678,21 +678,25 @@ def case_adc_full_scale_flag(make_core, n_samples=64, n_chirps=32):
 
 def case_combine_and_group(make_core, n_cpi=2, n_ch=4, n_chirps=32, n_samples=64, fmt="int16", mti_mode=0, seed=51, **kw):
     """Optional stages in front of / behind the CFAR: non-coherent integration over the channels
-    (one combined map per CPI, fused into the Doppler stage) and peak grouping of the detections.
+    (one combined map per CPI, fused into the Doppler stage), coherent beams (steered channel sums in front of the
+    Doppler transform = an angle DFT over the channels, one map per beam) and peak grouping of the detections.
     Combined map within MAP_TOL of the oracle's; CFAR (+ grouping) on the GPU's own map bit-exact against the
     oracle's CFAR (+ grouping) on that same map; end-to-end list identical outside near-threshold cells."""
     cube, _ = st.synthetic_cube(n_cpi, n_ch, n_chirps, n_samples, seed=seed, dtype=fmt, n_targets=(2, 4))
-    for combine, group in (("nci", False), ("nci", True), ("none", True)):
+    n_beams = 1
+    while n_beams < n_ch:
+        n_beams <<= 1
+    for combine, group in (("nci", False), ("nci", True), ("none", True), ("beams", False), ("beams", True)):
         with make_core(n_range=n_samples, n_doppler=n_chirps, n_channels=n_ch, input_format=fmt, max_cpis=n_cpi,
                        mti_mode=mti_mode, combine=combine, peak_group=group, max_dets_per_cpi=1 << 16, **kw) as c:
             rd_map, dets, n_dets, status = (x.copy() for x in c.process(cube))
             tap = c.doppler_stage(c.range_stage(cube))                          # the stage tap combines too
             d_tap, c_tap, s_tap, dense = c.cfar_stage(rd_map)                    # CFAR stage tap on the combined maps
-        n_maps = 1 if combine == "nci" else n_ch
+        n_maps = {"nci": 1, "beams": n_beams}.get(combine, n_ch)
         assert rd_map.shape == (n_cpi, n_maps, n_samples, n_chirps) and np.array_equal(tap, rd_map)
         ref_map, ref_dets, ref_counts = fp.process_batch(cube, mti_mode=mti_mode, combine=combine, peak_group=group, **kw)
         err = float(np.abs(rd_map - ref_map).max())
-        assert err <= MAP_TOL * float(ref_map.max()), (combine, err)
+        assert err <= (2 if combine == "beams" else 1) * MAP_TOL * float(ref_map.max()), (combine, err / float(ref_map.max()))
         check_canonical(dets)
         assert int(n_dets.sum()) == len(dets) and status.tolist() == expected_status(cube)
         # bit-exact on the GPU's own map: CFAR, then grouping
