@@ -13,8 +13,9 @@ FEATURE = r"UTMALDG|UTMASTG|UTMAPF|UTMACMDFLUSH|UBLKCP|HSET2\.BF16|SYNCS|UCGABAR
 KERNELS = [
     ("K1 range stage, 512 samples, int16 input (the bench shape)", r"k1_range_kernelINS_7FftPlanILi512E.*EELi0EE"),
     ("K1 cluster variant, 4096 samples, complex64 (sharded mode)", r"k1_range_cluster_kernelINS_7FftPlanILi4096E.*EELi1EE"),
-    ("K2 Doppler stage, 256 chirps, alpha-max-beta-min", r"k2_doppler_kernelINS_7FftPlanILi256E.*EELi0ELb0E"),
-    ("K2 with non-coherent channel integration", r"k2_doppler_kernelINS_7FftPlanILi256E.*EELi0ELb1E"),
+    ("K2 Doppler stage, 256 chirps, alpha-max-beta-min", r"k2_doppler_kernelINS_7FftPlanILi256E.*EELi0ELi0EE"),
+    ("K2 with non-coherent channel integration", r"k2_doppler_kernelINS_7FftPlanILi256E.*EELi0ELi1EE"),
+    ("K2 with coherent beams", r"k2_doppler_kernelINS_7FftPlanILi256E.*EELi0ELi2EE"),
     ("K3 OS-CFAR, radar_core window (5,6,1,2), float", r"k3_cfar_kernelILi5ELi6ELi1ELi2ELi64ELi1ELi1ELb0E"),
     ("K3 OS-CFAR, integer mode", r"k3_cfar_kernelILi5ELi6ELi1ELi2ELi64ELi1ELi1ELb1E"),
     ("K3b peak grouping", r"k3b_peak_group"), ("K4 row offsets", r"k4_row_offsets"), ("K4 emit", r"k4_emit"),
