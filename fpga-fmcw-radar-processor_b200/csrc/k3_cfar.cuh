@@ -237,6 +237,9 @@ struct K3Shape {
         int n = (int)((227 * 1024) / (smem_bytes() + 1024));
         if (n > 2048 / THREADS) n = 2048 / THREADS;
         if (P0B > 1 && n > 3) n = 3;                                  // the wider phase 0 wants ~80 registers
+#ifdef RDP_K3_MAX_CTAS
+        if (n > RDP_K3_MAX_CTAS) n = RDP_K3_MAX_CTAS;                 // build-time experiment: fewer CTAs per SM, more registers each
+#endif
         return n < 1 ? 1 : n;
     }
 };

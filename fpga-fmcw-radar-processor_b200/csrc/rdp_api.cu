@@ -262,19 +262,21 @@ struct K3Generic {
     static K3Launcher get() { return K3Launcher{0, 0, 0, 0, 0, &prepare, &launch}; }
 };
 
-// `variant` (RDP_K3_VARIANT, A/B measurements of the default window only): 0 = 64-line tiles, one raw stage;
-// 1 = 64 lines, two stages; 2 = 32 lines, one stage; 3 = 32 lines, two stages; 4 / 5 = 64 lines, two / one stage(s),
-// phase 0 with two bands per thread on half of the warps
+// `variant` (RDP_K3_VARIANT, A/B measurements of the default window only): 0 = 64-line tiles, two raw stages (the
+// default since the phase-0 rewrite: three CTAs per SM with 85 registers and the next tile's TMA load under the
+// current tile beat four CTAs with 64 registers, 9.22 against 9.56 ms per 1024 automotive CPIs); 1 = 64 lines, one
+// stage; 2 = 32 lines, one stage; 3 = 32 lines, two stages; 4 / 5 = 64 lines, two / one stage(s), phase 0 with two
+// bands per thread on half of the warps
 K3Launcher k3_for(int hl, int hc, int gl, int gc, int variant) {
 #define RDP_K3_CASE(HL, HC, GL, GC, TR, NS) \
     if (hl == HL && hc == HC && gl == GL && gc == GC) return K3Inst<HL, HC, GL, GC, TR, NS>::get();
-    if (variant == 1) { RDP_K3_CASE(5, 6, 1, 2, 64, 2) }
+    if (variant == 1) { RDP_K3_CASE(5, 6, 1, 2, 64, 1) }
     if (variant == 2) { RDP_K3_CASE(5, 6, 1, 2, 32, 1) }
     if (variant == 3) { RDP_K3_CASE(5, 6, 1, 2, 32, 2) }
     if (variant == 4 && hl == 5 && hc == 6 && gl == 1 && gc == 2) return K3Inst<5, 6, 1, 2, 64, 2, 2>::get();
     if (variant == 5 && hl == 5 && hc == 6 && gl == 1 && gc == 2) return K3Inst<5, 6, 1, 2, 64, 1, 2>::get();
-    RDP_K3_CASE(5, 6, 1, 2, 64, 1)      // radar_core.vhd:376-382 defaults (4,4,2,1), as built
-    RDP_K3_CASE(6, 5, 2, 1, 64, 1)      // same, as named
+    RDP_K3_CASE(5, 6, 1, 2, 64, 2)      // radar_core.vhd:376-382 defaults (4,4,2,1), as built
+    RDP_K3_CASE(6, 5, 2, 1, 64, 2)      // same, as named
     RDP_K3_CASE(3, 4, 1, 1, 64, 1)      // tb_os_cfar_2d.vhd:16-19 (3,2,1,1), as built
     RDP_K3_CASE(4, 3, 1, 1, 64, 1)      // same, as named
     RDP_K3_CASE(3, 3, 1, 1, 64, 1)      // legacy quick config (2,2,1,1)
