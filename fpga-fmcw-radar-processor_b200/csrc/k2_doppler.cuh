@@ -104,10 +104,10 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
             for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) bacc[i] = make_float2(0.0f, 0.0f);
         }
       for (int ch = 0; ch < (COMBINE ? n_combine : 1); ++ch) {
-        float2 v[E];                                     // the line's samples after the notch, before the window
+        float2 v[E];                                     // the line's samples after the notch and (COMBINE != 2) the window
         if (mti_mode == 0) {
             RDP_UNROLL
-            for (int i = 0; i < E; ++i) v[i] = raw[i];
+            for (int i = 0; i < E; ++i) v[i] = COMBINE == 2 ? raw[i] : make_float2(raw[i].x * wv[i], raw[i].y * wv[i]);
         } else {                                         // doppler_notch.vhd:72-93, zero initial state (:99-102)
             const float2* src = x_rc + in_row(active ? row : 0, ch) * N;
             RDP_UNROLL
@@ -123,7 +123,8 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                         const float2 d2 = (active && n >= 2) ? __ldg(src + n - 2) : make_float2(0.f, 0.f);
                         s = make_float2(s.x - 2.0f * d1.x + d2.x, s.y - 2.0f * d1.y + d2.y);
                     }
-                    v[b * P0::R + r] = s;
+                    const float w = COMBINE == 2 ? 1.0f : wv[b * P0::R + r];
+                    v[b * P0::R + r] = COMBINE == 2 ? s : make_float2(s.x * w, s.y * w);
                 }
             }
         }
@@ -135,10 +136,8 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
             for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) bacc[i] = cadd(bacc[i], cmul(v[i], ph));
             if (ch + 1 < n_combine) continue;
             RDP_UNROLL
-            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) v[i] = bacc[i];
+            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) v[i] = make_float2(bacc[i].x * wv[i], bacc[i].y * wv[i]);   // the window, once per beam
         }
-        RDP_UNROLL
-        for (int i = 0; i < E; ++i) v[i] = make_float2(v[i].x * wv[i], v[i].y * wv[i]);
         Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
         if (COMBINE == 1) {
             RDP_UNROLL
