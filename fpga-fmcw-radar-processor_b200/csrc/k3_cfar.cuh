@@ -932,14 +932,15 @@ k3_cfar_generic_kernel(const float* __restrict__ rd_map, float* __restrict__ cfa
 __global__ void __launch_bounds__(256)
 k3b_peak_group_kernel(const uint32_t* __restrict__ bits_in, uint32_t* __restrict__ bits_out, const float* __restrict__ rd_map,
                       CfarArgs a, long long n_words) {
-    const long long w = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (w >= n_words) return;
-    const long long words_per_map = (long long)a.n_range * a.words_per_row;
-    const long long map = w / words_per_map;
-    const int line = (int)((w - map * words_per_map) / a.words_per_row), word = (int)(w % a.words_per_row);
-    const uint32_t* bm = bits_in + map * words_per_map;
-    const float* m = rd_map + map * (long long)a.n_range * a.n_doppler;
+    const unsigned w = blockIdx.x * 256u + threadIdx.x;            // n_words < 2^31 (the host caps the range lines of a launch)
+    if (w >= (unsigned)n_words) return;
     const uint32_t in = __ldg(bits_in + w);
+    if (in == 0u) { bits_out[w] = 0u; return; }                   // nearly every word: no index arithmetic at all
+    const unsigned words_per_map = (unsigned)a.n_range * (unsigned)a.words_per_row;
+    const unsigned map = w / words_per_map, in_map = w - map * words_per_map;
+    const int line = (int)(in_map / (unsigned)a.words_per_row), word = (int)(in_map - (unsigned)line * (unsigned)a.words_per_row);
+    const uint32_t* bm = bits_in + (size_t)map * words_per_map;
+    const float* m = rd_map + (size_t)map * a.n_range * a.n_doppler;
     uint32_t out = in, todo = in;
     while (todo) {
         const int b = __ffs(todo) - 1;
