@@ -40,15 +40,16 @@ __device__ __forceinline__ float magnitude(float2 z) {
 // COMBINE: 0 = one map per channel; 1 = non-coherent integration (above); 2 = coherent beams of a uniform linear array:
 // the n_combine channels of one (CPI, range line) are summed with the steering phases exp(-j 2 pi beam c / n_beams)
 // BEFORE the transform (it is linear, so this equals an angle FFT across the channels after it) and ONE Doppler
-// transform per beam follows; output lines are enumerated (cpi, range, beam) with the beam fastest, so that the
-// n_beams passes over a line's channels hit L1 / L2, and land in [cpi][beam][range][doppler].
+// transform per beam follows.  Beams b and b + n_beams / 2 differ by the sign of the odd channels only, so one pass over
+// the channels (even and odd channels summed separately) yields both: work items are (cpi, range, beam pair) with the
+// pair fastest, so that the n_beams / 2 passes over a line's channels hit L1 / L2; maps land in [cpi][beam][range][doppler].
 template <class Plan, int MAG, int COMBINE = 0>
 __global__ void __launch_bounds__(K2Shape<Plan>::THREADS)
 k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                   const float* __restrict__ window, const float2* __restrict__ twtab,
                   long long n_rows, int mti_mode, int rows_per_map, int pad_rows, int n_combine, int n_range,
                   int n_beams, const float2* __restrict__ steer) {
-    // COMBINE 1: n_rows counts OUTPUT lines (cpi, range); COMBINE 2: (cpi, range, beam).
+    // COMBINE 1: n_rows counts OUTPUT lines (cpi, range); COMBINE 2: work items (cpi, range, beam pair), n_beams >= 2.
     // Input line of channel c = (cpi * n_combine + c) * n_range + range.  steer[m] = exp(-j 2 pi m / n_beams).
     constexpr int N = Plan::N, E = Plan::E, T = Plan::T;
     constexpr int G = K2Shape<Plan>::G;
@@ -71,7 +72,8 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
 
     // software pipeline: the next line's samples are in flight during the butterflies
     float2 raw[E];
-    auto line_of = [&](long long row) -> long long { return COMBINE == 2 ? row / n_beams : row; };   // (cpi, range) index
+    const int n_pairs = n_beams > 1 ? n_beams / 2 : 1;
+    auto line_of = [&](long long row) -> long long { return COMBINE == 2 ? row / n_pairs : row; };   // (cpi, range) index
     auto in_row = [&](long long row, int ch) -> long long {
         if (COMBINE == 0) return row;
         const long long line = line_of(row), cpi = line / n_range;
@@ -92,16 +94,16 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
     for (long long row0 = (long long)blockIdx.x * G; row0 < n_rows; row0 += stride) {
         const long long row = row0 + gid;
         const bool active = row < n_rows;
-        const int beam = COMBINE == 2 ? (int)((active ? row : 0) % n_beams) : 0;
+        const int beam = COMBINE == 2 ? (int)((active ? row : 0) % n_pairs) : 0;     // the pair's first beam
         float macc[COMBINE == 1 ? E : 1];                            // COMBINE 1: sum of the channels' magnitudes
-        float2 bacc[COMBINE == 2 ? E : 1];                           // COMBINE 2: steered sum of the channels' samples
+        float2 bacc[COMBINE == 2 ? E : 1], bodd[COMBINE == 2 ? E : 1];   // COMBINE 2: steered sums of the even / odd channels
         if (COMBINE == 1) {
             RDP_UNROLL
             for (int i = 0; i < (COMBINE == 1 ? E : 1); ++i) macc[i] = 0.0f;
         }
         if (COMBINE == 2) {
             RDP_UNROLL
-            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) bacc[i] = make_float2(0.0f, 0.0f);
+            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) { bacc[i] = make_float2(0.0f, 0.0f); bodd[i] = make_float2(0.0f, 0.0f); }
         }
       for (int ch = 0; ch < (COMBINE ? n_combine : 1); ++ch) {
         float2 v[E];                                     // the line's samples after the notch and (COMBINE != 2) the window
@@ -132,11 +134,23 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
         else fetch(row + stride, 0);
         if (COMBINE == 2) {
             const float2 ph = __ldg(steer + ((beam * ch) & (n_beams - 1)));
-            RDP_UNROLL
-            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) bacc[i] = cadd(bacc[i], cmul(v[i], ph));
+            if (ch & 1) {
+                RDP_UNROLL
+                for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) bodd[i] = cadd(bodd[i], cmul(v[i], ph));
+            } else {
+                RDP_UNROLL
+                for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) bacc[i] = cadd(bacc[i], cmul(v[i], ph));
+            }
             if (ch + 1 < n_combine) continue;
+        }
+      // COMBINE 2: two transforms per pass over the channels -- beam (even + odd sums), then beam + n_beams / 2 (even - odd)
+      for (int half = 0; half < (COMBINE == 2 && n_beams > 1 ? 2 : 1); ++half) {
+        if (COMBINE == 2) {
             RDP_UNROLL
-            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) v[i] = make_float2(bacc[i].x * wv[i], bacc[i].y * wv[i]);   // the window, once per beam
+            for (int i = 0; i < (COMBINE == 2 ? E : 1); ++i) {
+                const float2 t = half ? csub(bacc[i], bodd[i]) : cadd(bacc[i], bodd[i]);
+                v[i] = make_float2(t.x * wv[i], t.y * wv[i]);          // the window, once per beam
+            }
         }
         Plan::template run<T>(v, tw, xbuf, parity, tid, gid);
         if (COMBINE == 1) {
@@ -148,8 +162,8 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
             // sharded mode: every map of rows_per_map lines is written with pad_rows halo lines above and below
             long long orow = rows_per_map > 0 ? row + (2 * (row / rows_per_map) + 1) * pad_rows : row;
             if (COMBINE == 2) {                                      // (cpi, range, beam) -> [cpi][beam][range]
-                const long long line = row / n_beams, cpi = line / n_range;
-                orow = (cpi * n_beams + beam) * n_range + (line - cpi * n_range);
+                const long long line = row / n_pairs, cpi = line / n_range;
+                orow = (cpi * n_beams + beam + half * n_pairs) * n_range + (line - cpi * n_range);
             }
             float* dst = rd_map + orow * N;
             RDP_UNROLL
@@ -159,6 +173,7 @@ k2_doppler_kernel(const float2* __restrict__ x_rc, float* __restrict__ rd_map,
                     dst[PL::out_index(tid, b, r)] = COMBINE == 1 ? macc[b * PL::R + r] : magnitude<MAG>(v[b * PL::R + r]);
             }
         }
+      }   // beams of the pair
       }   // channels
     }
 }

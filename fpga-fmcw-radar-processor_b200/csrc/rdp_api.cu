@@ -508,7 +508,9 @@ int run_doppler(rdp_handle* h, const float2* x_rc, int n_cpi, float* rd_map, lon
                 int rows_per_map = 0, int pad_rows = 0) {
     const rdp_config& c = h->cfg;
     const int combine = rows_override < 0 ? c.combine : RDP_COMBINE_NONE;
-    const long long rows = rows_override >= 0 ? rows_override : (long long)n_cpi * h->map_channels * c.n_samples;
+    // work items: output lines; with coherent beams one item yields the two beams of a pair
+    const int items_per_line = (combine == RDP_COMBINE_BEAMS && h->n_beams > 1) ? h->n_beams / 2 : h->map_channels;
+    const long long rows = rows_override >= 0 ? rows_override : (long long)n_cpi * items_per_line * c.n_samples;
     if (rows == 0) return RDP_OK;
     long long blocks = (rows + h->k2.G - 1) / h->k2.G;
     int grid = (int)(blocks < h->k2_grid_cap ? blocks : h->k2_grid_cap);
