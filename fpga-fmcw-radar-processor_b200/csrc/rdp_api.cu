@@ -3,7 +3,7 @@
 // Built two ways from the same source:
 //   nvcc -gencode arch=compute_100a,code=sm_100a ...      -> librdp.so      (the product)
 //   g++  -x c++ -DRDP_EMU ...                              -> librdp_emu.so  (CPU test harness
-//        for kernel logic only; see csrc/emu/cuda_emu.h -- never loaded by the product)
+//        for kernel logic only; see tests/emu/cuda_emu.h -- never loaded by the product)
 #include "../../include/rdp.h"
 #include "k1_range.cuh"
 #include "k2_doppler.cuh"

@@ -29,5 +29,16 @@ Pinning status (see DESIGN.md "Oracle"):
                             Pinned only structurally: forward DFT, natural
                             order, golden_input_chirp.txt peak at bin 290,
                             radar_output.txt target rows {99..101},{499..501}.
+  * rtl_fixed.bfp_fft, process_cpi_fixed
+                            PARITY UNPINNED for the two FFT stages: a
+                            SELF-DEFINED 16-bit block-floating-point transform
+                            (the IP's word widths and convergent rounding, not
+                            its netlist) chained with the pinned stages above;
+                            librdp's arith = FIXED16 is bit-exact against it
+                            ("self-consistent, not Xilinx-exact").
+  * float_path.peak_group, combine = "nci" / "beams"
+                            not in the reference at all: the
+                            rules librdp's optional stages implement, stated here
+                            so that they can be tested.
 """
 from . import rtl_fixed, float_path, stimulus  # noqa: F401

@@ -1,5 +1,5 @@
 """Kernel LOGIC under host emulation (CPU, no GPU): the same kernel sources as librdp.so,
-compiled with g++ against csrc/emu/cuda_emu.h (one OS thread per CUDA thread), driven through
+compiled with g++ against tests/emu/cuda_emu.h (one OS thread per CUDA thread), driven through
 the same C ABI and compared with the oracle at tiny sizes.  This is a development aid that
 catches indexing / counting mistakes before GPU time is spent; it is not a product path
 (the product loader refuses this library) and proves nothing about the real device -- the GPU
