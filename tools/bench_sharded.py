@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 import fpga_fmcw_radar_processor_b200 as rdp
-from oracle import stimulus as st            # synthetic input generator only
+from fpga_fmcw_radar_processor_b200 import scenario as st      # synthetic input generator
 
 
 def main():
@@ -43,7 +43,7 @@ def main():
     cube, _ = st.synthetic_cube(uniq, 1, nc, ns, seed=404, dtype="complex64", n_targets=(3, 5), sigma=40.0)
     local_cube = np.ascontiguousarray(cube[:, :, rank * cl:(rank + 1) * cl])
     local_cube = np.concatenate([local_cube] * (B // uniq), axis=0) if B > uniq else local_cube[:B]
-    ex = rdp.TorchExchange()
+    ex = rdp.SocketExchange(port_offset=7)       # IPC handles + barriers over TCP sockets (the product package is torch-free)
     sh = rdp.ShardedCpi(n_chirps=nc, n_samples=ns, world=world, rank=rank, n_channels=1, n_cpi=B, input_format="complex64",
                         device=local, max_dets_per_cpi=1 << 14, **kw)
     d_in = sh.upload_local(local_cube)
@@ -80,13 +80,14 @@ def main():
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"large_{nc}x{ns}x1ch_complex64_sharded_cpi", "cpis_per_step": B, "cfar": "ref 8/8 guard 4/2 (N_REF 480)",
                            "sharding": "chirps -> (K1 peer stores over NVLink, CUDA IPC) -> range lines; CFAR halo lines copied from the neighbours",
-                           "barriers": "torch.distributed (NCCL), host-driven, 4 per step"},
+                           "barriers": "TCP sockets (exchange.SocketExchange), host-driven, 4 per step; torch.distributed only for this script's own timing"},
                 "all_to_all": {"bytes_per_cpi": a2a_bytes, "gbs_sustained": a2a_bytes * cpis / 1e9,
                                "gbs_during_range_stage_per_gpu": (a2a_bytes / world) * B / (ph["range_scatter"] * 1e-3) / 1e9},
                 "phase_ms_rank0": ph, "detections_per_step": int(sum(n_dets))}
         print(json.dumps(line), flush=True)
     d_in.free()
     sh.close()
+    ex.close()
     dist.barrier()
     dist.destroy_process_group()
 
