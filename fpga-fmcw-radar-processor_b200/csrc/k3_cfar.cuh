@@ -231,7 +231,7 @@ struct K3Shape {
     static_assert(4 * NCOV >= 2 * HC + 1 + 3 && 4 * NCOV >= 2 * HC + 2 + (HC % 2 ? 3 : 2), "NCOV groups cover the window at any alignment");
     static constexpr size_t smem_bytes() {
         return sizeof(float) * ((size_t)NSTAGE * TF_WORDS + SR * NG) + sizeof(uint32_t) * (2 * PLANE + TR * TWORDS) +
-               sizeof(unsigned short) * (N_STRIPS + SURV_CAP) + sizeof(int) * (8 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
+               sizeof(unsigned short) * (N_STRIPS + SURV_CAP) + sizeof(int) * (12 + 2 * NSLOT) + 2 * sizeof(unsigned long long) + 128;
     }
     static constexpr int occupancy_hint() {                        // CTAs per SM the shared memory allows (<= 2048 threads)
         int n = (int)((227 * 1024) / (smem_bytes() + 1024));
@@ -301,7 +301,10 @@ template <int HL, int HC, int GL, int GC, int TR, int NSTAGE, int P0B, bool INT_
 __global__ void __launch_bounds__((K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>::THREADS), (K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>::occupancy_hint()))
 k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, uint32_t* __restrict__ det_bits,
                CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
-               const RDP_GRID_CONSTANT CUtensorMap tmap, uint32_t* __restrict__ cpi_flags) {
+               const RDP_GRID_CONSTANT CUtensorMap tmap, uint32_t* __restrict__ cpi_flags, int* __restrict__ tile_queue) {
+    // tile_queue (nullable): a counter zeroed before the launch.  The persistent CTAs take their first tile by index and
+    // every later one from the queue (gridDim.x + atomicAdd), one tile ahead so that its TMA load can be issued early:
+    // tiles differ several-fold in cost (crowded CPIs), and a fixed stride leaves the slowest CTA ~10 % behind.
     // cpi_flags (nullable, INT_MODE): word [map / n_channels] |= RDP_STATUS_MAP_RANGE when a tile holds a magnitude word
     // >= 2^24 (the packed pre-filter converts words to float and is only conservative while that is exact)
     using Sh = K3Shape<HL, HC, GL, GC, TR, NSTAGE, P0B>;
@@ -315,7 +318,7 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     float* cov = reinterpret_cast<float*>(planes + 2 * PLANE);                  // [SR][NG] sums of the 4 NCOV columns from group g on
     uint32_t* bits = reinterpret_cast<uint32_t*>(cov + SR * NG);                // [TR][TWORDS]
     int* ctr = reinterpret_cast<int*>(bits + TR * Sh::TWORDS);                  // 0: strips listed, 1: survivors listed, 2 / 3: tile holds a negative word (by iteration parity)
-    int* wtab = ctr + 8;                                                        // [NSLOT][2]: tf index = ctr * mul + add
+    int* wtab = ctr + 12;                                                       // [NSLOT][2]: tf index = ctr * mul + add  (ctr[8], ctr[9]: the next tile, by parity)
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(wtab + 2 * Sh::NSLOT);
     unsigned short* strips = reinterpret_cast<unsigned short*>(mbar + 2);       // band * 64 + column
     unsigned short* surv = strips + Sh::N_STRIPS;                               // tile line * 64 + column
@@ -384,7 +387,15 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
 #endif
     int iter = 0;
     const int n_tiles32 = (int)n_tiles;
-    for (int tile_id = blockIdx.x; tile_id < n_tiles32; tile_id += gridDim.x, ++iter) {
+    int next_tile = (int)blockIdx.x;
+    for (int tile_id = blockIdx.x; tile_id < n_tiles32; tile_id = next_tile, ++iter) {
+    // the tile after this one: thread 0 draws it now (before the first barrier of the iteration) and publishes it in
+    // ctr[8 + parity]; everybody reads it after the last barrier
+    if (tile_queue != nullptr) {
+        if (threadIdx.x == 0) { next_tile = (int)gridDim.x + atomicAdd(tile_queue, 1); ctr[8 + (iter & 1)] = next_tile; }
+    } else {
+        next_tile = tile_id + (int)gridDim.x;
+    }
     const int stage = (use_tma && NSTAGE == 2) ? (iter & 1) : 0;
     float* tf = tf0 + stage * Sh::TF_WORDS;
     const long long map = tile_id / tiles_per_map;
@@ -399,9 +410,9 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
         // two stages: the next tile is fetched into the other stage (its readers finished before the barrier that
         // ended the previous iteration) while this one is processed; one stage: it was issued at the end of the
         // previous iteration and other CTAs of the SM cover the latency
-        if (NSTAGE == 2 && threadIdx.x == 0 && tile_id + (int)gridDim.x < n_tiles32) issue(tile_id + gridDim.x, stage ^ 1);
+        if (NSTAGE == 2 && threadIdx.x == 0 && next_tile < n_tiles32) issue(next_tile, stage ^ 1);
         // one stage: the next tile cannot land in shared memory yet, but it can be on its way into L2
-        if (NSTAGE == 1 && (a.debug_skip & 8) == 0 && threadIdx.x == 32 && tile_id + (int)gridDim.x < n_tiles32) prefetch(tile_id + gridDim.x);
+        if (NSTAGE == 1 && (a.debug_skip & 8) == 0 && tile_queue == nullptr && threadIdx.x == 32 && next_tile < n_tiles32) prefetch(next_tile);
         mbar_wait(mbar + stage, (uint32_t)((NSTAGE == 2 ? (iter >> 1) : iter) & 1));
     } else
 #endif
@@ -878,8 +889,9 @@ k3_cfar_kernel(const float* __restrict__ rd_map, float* __restrict__ cfar_out, u
     __syncthreads();
     }
     // every read of this tile's raw stage, planes and lists lies before a barrier every thread has passed
+    if (tile_queue != nullptr) next_tile = ctr[8 + (iter & 1)];   // published before this iteration's first barrier
 #ifndef RDP_EMU
-    if (use_tma && NSTAGE == 1 && threadIdx.x == 0 && tile_id + (int)gridDim.x < n_tiles32) issue(tile_id + gridDim.x, 0);
+    if (use_tma && NSTAGE == 1 && threadIdx.x == 0 && next_tile < n_tiles32) issue(next_tile, 0);
 #endif
     // bitmask of this tile: rows r0.., words (c0 / 32)..  (TC is a multiple of 32 so tiles own whole words)
     uint32_t* bm = det_bits + map * (long long)a.n_range * a.words_per_row;

@@ -64,7 +64,7 @@ struct K3Launcher {
     cudaError_t (*prepare)(size_t smem, int* ctas_per_sm);
     void (*launch)(long long grid, size_t smem, cudaStream_t st, const float* rd_map, float* cfar_out,
                    uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
-                   const CUtensorMap* tmap, uint32_t* cpi_flags);
+                   const CUtensorMap* tmap, uint32_t* cpi_flags, int* tile_queue);
 };
 
 template <class K>
@@ -238,13 +238,13 @@ struct K3Inst {
     }
     static void launch(long long grid, size_t s, cudaStream_t st, const float* rd_map, float* cfar_out,
                        uint32_t* det_bits, CfarArgs a, int tiles_r, int tiles_c, long long n_tiles, int use_tma,
-                       const CUtensorMap* tmap, uint32_t* cpi_flags) {
+                       const CUtensorMap* tmap, uint32_t* cpi_flags, int* tile_queue) {
         if (a.int_mode)
             RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, P0B, true>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
-                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap, cpi_flags);
+                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap, cpi_flags, tile_queue);
         else
             RDP_LAUNCH((k3_cfar_kernel<HL, HC, GL, GC, TR, NSTAGE, P0B, false>), (unsigned)grid, Sh::THREADS, s, st, rd_map, cfar_out,
-                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap, cpi_flags);
+                       det_bits, a, tiles_r, tiles_c, n_tiles, use_tma, *tmap, cpi_flags, tile_queue);
     }
     static K3Launcher get() {
         return K3Launcher{TR, Sh::TC, Sh::SR, Sh::SC, Sh::smem_bytes(), &prepare, &launch};
@@ -253,7 +253,7 @@ struct K3Inst {
 struct K3Generic {
     static cudaError_t prepare(size_t, int* occ) { if (occ) *occ = 64; return cudaSuccess; }
     static void launch(long long grid, size_t, cudaStream_t st, const float* rd_map, float* cfar_out,
-                       uint32_t* det_bits, CfarArgs a, int, int, long long, int cap, const CUtensorMap*, uint32_t*) {
+                       uint32_t* det_bits, CfarArgs a, int, int, long long, int cap, const CUtensorMap*, uint32_t*, int*) {
         long long n_words = grid;   // grid carries the bitmask word count for the generic kernel, `use_tma` its CTA cap
         long long blocks = (n_words + 7) / 8;
         if (blocks > cap) blocks = cap;
@@ -346,6 +346,8 @@ struct rdp_handle {
     int knob_k3_debug_skip = 0, knob_k3_skew_ns = 0;
     int knob_k1_cluster = -1;       // RDP_K1_CLUSTER: -1 = automatic (sharded mode only), 0 / 1 = forced off / on
     int stream_spec_dets = kStreamSpecDets;
+    int knob_k3_queue = 1;          // RDP_K3_QUEUE: K3's persistent CTAs draw their tiles from a device-side queue
+    int* k3_queue = nullptr;
     int knob_stream_graph = 1;      // RDP_STREAM_GRAPH: streaming submissions replay a CUDA graph of their kernel chain
     int k3_variant = 0;             // RDP_K3_VARIANT (tile shape / staging depth of the default CFAR window, A/B measurements)
     void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled, resolved at create (NULL: manual tile loads)
@@ -558,7 +560,7 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
     std::memset(&tmap, 0, sizeof(tmap));
     if (h->k3.trows == 0) {
         h->k3.launch(maps * c.n_samples * args.words_per_row, 0, h->cur, rd_map, cfar_out, h->det_bits, args, 0, 0,
-                     0, h->k3_grid_cap, &tmap, nullptr);
+                     0, h->k3_grid_cap, &tmap, nullptr, nullptr);
     } else {
         const int tiles_r = (c.n_samples + h->k3.trows - 1) / h->k3.trows;
         const int tiles_c = (c.n_chirps + h->k3.tcols - 1) / h->k3.tcols;
@@ -590,8 +592,14 @@ int run_cfar(rdp_handle* h, const float* rd_map, int n_cpi, float* cfar_out, rdp
             const long long want = (n_tiles + h->knob_k3_tiles_per_cta - 1) / h->knob_k3_tiles_per_cta;
             if (want > grid) grid = want;
         }
+        // tiles differ several-fold in cost: the persistent CTAs draw them from a queue (RDP_K3_QUEUE=0: fixed stride)
+        int* queue = nullptr;
+        if (h->knob_k3_queue && h->k3_queue && n_tiles > grid) {
+            RDP_CUDA(h, cudaMemsetAsync(h->k3_queue, 0, sizeof(int), h->cur));
+            queue = h->k3_queue;
+        }
         h->k3.launch(grid, h->k3.smem, h->cur, rd_map, cfar_out, h->det_bits, args, tiles_r, tiles_c, n_tiles, use_tma,
-                     &tmap, int_mode ? cpi_flags : nullptr);
+                     &tmap, int_mode ? cpi_flags : nullptr, queue);
     }
     stage_end(h);
     int rc = launch_check(h, "k3_cfar_kernel");
@@ -840,7 +848,7 @@ void release(rdp_handle* h) {
     if (h->t1) cudaEventDestroy(h->t1);
     void* ptrs[] = {h->win_r, h->win_d, h->tw_r, h->tw_d, h->x_rc, h->map_scratch[0], h->map_scratch[1],
                     h->in_stage[0], h->in_stage[1], h->det_bits, h->row_off, h->rom_dev, h->sat_dev, h->trk_state, h->counts, h->status, h->dets, h->packed, h->l2_flush,
-                    h->cpi_flags[0], h->cpi_flags[1], h->det_bits2, h->steer, h->rom_r, h->rom_d, h->btw_r, h->btw_d, h->exp_r, h->exp_d, h->btw_tap};
+                    h->cpi_flags[0], h->cpi_flags[1], h->det_bits2, h->steer, h->k3_queue, h->rom_r, h->rom_d, h->btw_r, h->btw_d, h->exp_r, h->exp_d, h->btw_tap};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -893,6 +901,7 @@ int init_handle(rdp_handle* h) {
         if ((e = std::getenv("RDP_K3_SKEW_NS"))) h->knob_k3_skew_ns = std::atoi(e);
         if ((e = std::getenv("RDP_STREAM_SPEC")) && std::atoi(e) > 0) h->stream_spec_dets = std::atoi(e);
         if ((e = std::getenv("RDP_STREAM_GRAPH"))) h->knob_stream_graph = std::atoi(e);
+        if ((e = std::getenv("RDP_K3_QUEUE"))) h->knob_k3_queue = std::atoi(e);
     }
     // the FFT kernels (HBM-bound) run on `stream`, the CFAR kernels (ALU-bound) of the previous chunk on `cfar_stream`;
     // the FFT stream has the higher priority so that its CTAs are placed first whenever CFAR CTAs retire
@@ -1056,6 +1065,8 @@ int init_handle(rdp_handle* h) {
         rc = dev_alloc(h, &h->cpi_flags[i], (size_t)chunk);
         if (rc) return rc;
     }
+    rc = dev_alloc(h, &h->k3_queue, 4);
+    if (rc) return rc;
     if (c.arith == RDP_ARITH_FIXED16) {
         if (h->k3.trows == 0) return fail(h, RDP_E_INVALID, "arith FIXED16: no tiled integer CFAR instance for this window shape");
         rc = ensure_fixed_tables(h);

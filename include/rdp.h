@@ -186,6 +186,7 @@ typedef struct rdp_info {
  *                         peer-store corner turn of rdp_range_stage_scatter with 2048- / 4096-sample chirps)
  *   RDP_STREAM_SPEC=n     records per CPI a streaming slot copies back together with the counts (tests)
  *   RDP_STREAM_GRAPH=0|1  streaming submissions replay a CUDA graph of their kernel chain (default 1)
+ *   RDP_K3_QUEUE=0|1      the persistent CFAR CTAs draw their tiles from a device-side queue (default 1) / fixed stride
  *   RDP_K1_TMA=0|1        force the TMA tile store of the range stage off / on (default: on for int16 input)       */
 typedef struct rdp_handle rdp_handle;
 
