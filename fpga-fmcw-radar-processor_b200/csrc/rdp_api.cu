@@ -319,7 +319,7 @@ struct rdp_handle {
     cudaStream_t cfar_stream = nullptr;    // overlap mode: K3/K4 of chunk i run here while K1/K2 of chunk i+1 run on `stream`
     cudaStream_t cur = nullptr;            // stream the run_* helpers launch on
     cudaEvent_t ev_map_ready[2] = {nullptr, nullptr}, ev_cfar_done[2] = {nullptr, nullptr};
-    int overlap = 1;
+    int overlap = 0;               // RDP_OVERLAP: with the K3 tile queue the two-stream pipeline costs 1.7 % (measured), so it is opt-in
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     std::vector<cudaEvent_t> ev_copied, ev_done, ev_mapout, ev_counts;
     float *win_r = nullptr, *win_d = nullptr;

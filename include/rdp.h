@@ -180,7 +180,8 @@ typedef struct rdp_info {
 } rdp_info;
 
 /* Environment variables read by rdp_create (measurement knobs; the defaults are what the benchmarks use):
- *   RDP_OVERLAP=0|1       CFAR kernels of chunk i on a second stream under the FFT kernels of chunk i+1 (default 1)
+ *   RDP_OVERLAP=0|1       CFAR kernels of chunk i on a second stream under the FFT kernels of chunk i+1 (default 0:
+ *                         since K3 balances its tiles through a queue there is no tail left to fill, measured -1.7 %)
  *   RDP_K3_CTAS=n         cap the persistent CFAR CTAs per SM;  RDP_K12_CTAS=n  the same for the two FFT kernels
  *   RDP_K1_CLUSTER=0|1    force the thread-block-cluster variant of the range stage off / on (default: only for the
  *                         peer-store corner turn of rdp_range_stage_scatter with 2048- / 4096-sample chirps)
